@@ -1,0 +1,264 @@
+"""Pin the CPU oracle against the reference's own golden vectors and known-answer tests.
+
+Golden vectors: tests/golden/reference_csv_fts.json (made by tests/golden/make_golden.py from
+/root/reference/benchmark/results/timings*.csv).  KATs: /root/reference/test/*.jl (cited inline).
+These run on CPU; the oracle is test infrastructure only.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from fts_oracle import FAMILIES as F
+from problems import CSV_PROBLEMS, CSV_RTOL, CSV_RTOL_AVX_DEFAULT, CSV_RTOL_DEFAULT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_csv_fts.json")))
+PI = math.pi
+
+
+def _rows(kinds):
+    seen = set()
+    for r in GOLD["rows"]:
+        key = (r["function"], r["kind"], r["value"])
+        if r["kind"] in kinds and key not in seen:
+            seen.add(key)
+            yield r
+
+
+@pytest.fixture(scope="module")
+def caches(oracle):
+    ml = GOLD["settings"]["max_levels"]
+    return {1: oracle.cache1d("f64", ml["1"]), 2: oracle.cache_tensor("f64", 2, ml["2"]),
+            3: oracle.cache_tensor("f64", 3, ml["3"])}
+
+
+@pytest.mark.parametrize("row", list(_rows({"adaptive", "quad"})), ids=lambda r: f"{r['function']}-{r['kind']}-{r['source'].split('/')[-1]}")
+def test_adaptive_rows_match_reference_values(oracle, caches, row):
+    """adaptive_integrate_{1,2,3}D and quad (same kernel, quad.jl:49,117,155) at the benchmark
+    settings reproduce the reference's printed values, at the reference's stop level."""
+    dim, fam, p, low, up = CSV_PROBLEMS[row["function"]]
+    s = GOLD["settings"]
+    ml = s["max_levels"][str(dim)]
+    if dim == 1:
+        r = oracle.adaptive1d("f64", fam, p, low, up, s["rtol"], s["atol"], ml, caches[1])
+    else:
+        r = oracle.adaptive_nd("f64", dim, fam, p, low, up, s["rtol"], s["atol"], ml, caches[dim])
+    gold = float(row["value"])
+    rtol = CSV_RTOL.get((row["function"], row["kind"]), CSV_RTOL_DEFAULT)
+    assert abs(r.value - gold) <= rtol * abs(gold), (r, gold)
+    # the avx row of the same problem records the level the adaptive path stopped at
+    lvl = [x for x in GOLD["rows"] if x["function"] == row["function"] and x["kind"] == "avx"][0]
+    assert r.level == lvl["adaptive_level"]
+    assert r.converged == (not lvl["max_levels_reached"])
+
+
+@pytest.mark.parametrize("row", list(_rows({"avx"})), ids=lambda r: f"{r['function']}-{r['source'].split('/')[-1]}")
+def test_fixed_grid_rows_match_reference_values(oracle, row):
+    """integrate{1,2,3}D_avx at N=2^(level+2): the oracle's sequential and exactly-summed
+    fixed-grid values bracket the reference's reassociated @turbo value."""
+    dim, fam, p, low, up = CSV_PROBLEMS[row["function"]]
+    x, w, h = oracle.tanhsinh("f64", row["N"])
+    gold = float(row["value"])
+    rtol = CSV_RTOL.get((row["function"], "avx"), CSV_RTOL_AVX_DEFAULT)
+    for dt in ("f64", "f64x"):
+        v = oracle.integrate1d(dt, fam, p, low, up, x, w, h) if dim == 1 else \
+            oracle.integrate_nd(dt, dim, fam, p, low, up, x, w, h)
+        assert abs(v - gold) <= rtol * abs(gold), (dt, v, gold)
+
+
+def test_avx_singular_row_pinned_with_contraction(oracle):
+    """With 1-x^2 contracted into an FMA (what @turbo emits) the 1D endpoint-singular avx row
+    is reproduced to the last digit (timings_julia1.12.csv:13)."""
+    x, w, h = oracle.tanhsinh("f64", 32)
+    oracle.lib.fts_or_set_contract(1)
+    try:
+        v = oracle.integrate1d("f64x", F["F1_INVSQRT1MX2"], None, -1.0, 1.0, x, w, h)
+    finally:
+        oracle.lib.fts_or_set_contract(0)
+    assert abs(v - 3.141592650673913) <= 2 * np.spacing(3.14)
+
+
+# ------------------------------------------------------------------ primitive KATs (test/core.jl)
+def test_windows(oracle):
+    # SURVEY §8 a2 / test/caches.jl:17-18: tm values
+    assert oracle.tmax("f64", 1) == oracle.t_x_max("f64")
+    assert abs(oracle.t_x_max("f64") - 3.172644956372939) < 1e-15
+    assert np.allclose([oracle.t_w_max("f64", d) for d in (1, 2, 3)], [6.1216, 5.4367, 5.0387], atol=5e-5)
+    assert abs(oracle.t_x_max("f32") - 2.4088976) < 1e-6
+    assert np.allclose([oracle.t_w_max("f32", d) for d in (1, 2, 3)], [4.0765, 3.4256, 3.0566], atol=5e-5)
+    for d in (1, 2, 3):  # test/core.jl:34-36
+        assert oracle.tmax("f64", d) == min(oracle.t_x_max("f64"), oracle.t_w_max("f64", d))
+
+
+def test_primitive_identities(oracle):
+    t = 1.75  # test/core.jl:2-14
+    xt = oracle.prim("ordinate", "f64", t)
+    assert oracle.prim("ordinate", "f64", -t) == -xt
+    assert oracle.prim("weight", "f64", -t) == oracle.prim("weight", "f64", t)
+    ct = oracle.prim("ordinate_complement", "f64", t)
+    assert abs(ct - (1 - abs(xt))) <= 1e-16 + 1e-12 * ct
+    assert abs(oracle.prim("inv_ordinate", "f64", xt) - t) < 1e-13
+    # saturation guards, test/core.jl:17-25
+    assert oracle.prim("ordinate", "f64", 50.0) == np.nextafter(1.0, 0.0)
+    assert oracle.prim("ordinate", "f64", -50.0) == -np.nextafter(1.0, 0.0)
+    assert oracle.prim("weight", "f64", 8.0) == 0.0
+
+
+def test_tanhsinh_shapes(oracle):
+    # test/core.jl:38-57: n = N div 2 for odd and even N; last node is exactly tm
+    for N, n in ((79, 39), (80, 40), (11, 5), (10, 5)):
+        x, w, h = oracle.tanhsinh("f64", N)
+        assert len(x) == n and len(w) == n and h > 0
+        assert np.all(np.diff(x) >= 0) and np.all(x < 1) and np.all(w >= 0)
+    x32, w32, h32 = oracle.tanhsinh("f32", 8)
+    assert x32.dtype == np.float32 and len(x32) == 4
+
+
+def test_cache_shapes_and_quirks(oracle):
+    # test/caches.jl:8-18
+    c = oracle.cache1d("f64", 3)
+    cc = oracle.cache1d("f64", 3, complement=True)
+    assert len(c["xs"]) == 2 + 4 + 8 and c["tm"][0] == oracle.tmax("f64", 1)
+    assert cc["tm"][0] == oracle.t_w_max("f64", 1)
+    # outermost complement-window weights are exactly 0, c(tm) is subnormal
+    # (the node t == tm is the second initial node, caches.jl:66-69)
+    assert cc["iw"][1] == 0.0 and 0 < cc["ic"][1] < 2.3e-308
+    # 1D caches store only new (odd) nodes; tensor caches store all nodes
+    t = oracle.cache_tensor("f64", 2, 3)
+    assert len(t["xs"]) == 4 + 8 + 16
+    assert np.array_equal(t["xs"][0:4][0::2], c["xs"][0:2])  # level-1 odd tensor nodes == 1D level 1
+
+
+# ------------------------------------------------------------------ analytic KATs (test/*.jl)
+def test_kat_1d_fixed_grid(oracle):
+    # test/families_1d.jl:12-16 (N=120) ; test/runtests.jl:101-110 (N=80)
+    x, w, h = oracle.tanhsinh("f64", 120)
+    assert abs(oracle.integrate1d("f64", F["F1_POLY6"], None, -1, 1, x, w, h) - 9 / 7) < 1e-12
+    assert abs(oracle.integrate1d("f64", F["F1_RUNGE"], [25.0], -1, 1, x, w, h) - 2 * math.atan(5.0) / 5) < 1e-6
+    assert abs(oracle.integrate1d("f64", F["F1_EXP"], None, -1, 1, x, w, h) - (math.e - 1 / math.e)) < 1e-12
+    assert abs(oracle.integrate1d("f64", F["F1_LOG1MX"], None, -1, 1, x, w, h) - (2 * math.log(2) - 2)) < 1e-11
+    x, w, h = oracle.tanhsinh("f64", 80)
+    for coeffs in ([1.0], [1.0, 1.0], [0, 0, 3.0]):
+        assert abs(oracle.integrate1d("f64", F["F1_POLY7"], coeffs, -1, 1, x, w, h) - 2.0) < 1e-12
+    # config A of BASELINE.json: exp on [0,1] (README.md:174-181)
+    assert abs(oracle.integrate1d("f64", F["F1_EXP"], None, 0, 1, x, w, h) - (math.e - 1)) < 1e-13
+    # test/dispatch.jl:36: sin^2 on [0,pi] = pi/2
+    assert abs(oracle.integrate1d("f64", F["F1_SIN2"], [1.0], 0.0, PI, x, w, h) - PI / 2) < 1e-12
+
+
+def test_kat_1d_adaptive(oracle):
+    c = oracle.cache1d("f64", 16)
+    # test/families_1d.jl:22-26 (rtol=1e-12)
+    for fam, p, exact, tol in ((F["F1_POLY6"], None, 9 / 7, 1e-12), (F["F1_RUNGE"], [25.0], 2 * math.atan(5.0) / 5, 1e-12),
+                               (F["F1_EXP"], None, math.e - 1 / math.e, 1e-12), (F["F1_LOG1MX"], None, 2 * math.log(2) - 2, 1e-11)):
+        r = oracle.adaptive1d("f64", fam, p, -1.0, 1.0, 1e-12, 0.0, 16, c)
+        assert r.converged and abs(r.value - exact) < tol
+    # test/runtests.jl:205-208
+    r = oracle.adaptive1d("f64", F["F1_EXP"], None, 0.0, 1.0, 1e-8, 0.0, 16, c)
+    assert abs(r.value - (math.e - 1)) < 1e-8
+    # test/families_1d.jl:48-51 oscillatory; default rtol sqrt(eps) (core.jl:32-40)
+    r = oracle.adaptive1d("f64", F["F1_SIN2"], [1000.0], -PI, PI, math.sqrt(np.finfo(float).eps), 0.0, 16, c)
+    assert abs(r.value - PI) < 1e-10
+    r = oracle.adaptive1d("f64", F["F1_SIN2"], [1000.0], -PI, PI, 1e-12, 0.0, 10, c)
+    assert not r.converged and r.level == 10  # warn path
+    # max_levels = 0 returns the 5-point base estimate (test/dispatch.jl:10-25)
+    r = oracle.adaptive1d("f64", F["F1_EXP"], None, 0.0, 1.0, 1e-8, 0.0, 0, c)
+    assert r.level == 0 and not r.converged and math.isfinite(r.value) and r.value > 0 and r.evals == 5
+
+
+def test_kat_complement(oracle):
+    c = oracle.cache1d("f64", 20, complement=True)
+    # test/families_1d.jl:26, test/runtests.jl:416-425
+    r = oracle.adaptive1d_cmpl("f64", F["C1_INVSQRT"], [1.0], -1.0, 1.0, 1e-12, 0.0, 16, c)
+    assert abs(r.value - PI) < 1e-12
+    r = oracle.adaptive1d_cmpl("f64", F["C1_INVSQRT"], [1.0], -2.5, 3.25, 1e-12, 0.0, 16, c)
+    assert abs(r.value - PI) < 1e-12
+    # test/families_1d.jl:32-38
+    a, b = -2.5, 3.25
+    exact = (b - a) * (math.log(b - a) - 1)
+    for fam in (F["C1_LOG_BMX"], F["C1_LOG_XMA"]):
+        r = oracle.adaptive1d_cmpl("f64", fam, None, a, b, 1e-12, 0.0, 16, c)
+        assert abs(r.value - exact) < 1e-12
+    # test/families_1d.jl:40-44
+    r = oracle.adaptive1d_cmpl("f64", F["C1_EXP_INV_BMX"], None, 0.0, 1.0, 1e-14, 0.0, 20, c)
+    assert abs(r.value - 0.1484955067759220479) < 1e-14
+
+
+def test_kat_2d_3d(oracle):
+    x, w, h = oracle.tanhsinh("f64", 80)
+    # test/families_2d.jl:5-8, 16-23, 32
+    assert abs(oracle.integrate_nd("f64", 2, F["F2_POLY2"], [1, 0, 0, 1, 0, 1], [-1, -1], [1, 1], x, w, h) - 20 / 3) < 1e-12
+    a, b, c, d = -2.0, 3.0, -1.0, 2.0
+    exact = ((b ** 3 - a ** 3) / 3) * (d - c) + ((d ** 2 - c ** 2) / 2) * (b - a)
+    assert abs(oracle.integrate_nd("f64", 2, F["F2_POLY2"], [0, 0, 1, 1, 0, 0], [a, c], [b, d], x, w, h) - exact) < 1e-11
+    assert abs(oracle.integrate_nd("f64", 2, F["F2_POLY2"], [1, 0, 0, 0, 0, 0], [0, 0], [PI, PI], x, w, h) - PI ** 2) < 1e-12
+    # orientation by bound order, test/families_2d.jl:37-44
+    assert abs(oracle.integrate_nd("f64", 2, F["F2_POLY2"], [1, 0, 0, 0, 0, 0], [1, -1], [0, 2], x, w, h) - (-3.0)) < 1e-12
+    # 3D, test/families_3d.jl:1-22 (N=60) and 24-49 (anisotropic box, N=80)
+    x6, w6, h6 = oracle.tanhsinh("f64", 60)
+    assert abs(oracle.integrate_nd("f64", 3, F["F3_POLY2"], [1, 0, 0, 0, 0, 0], [-1] * 3, [1] * 3, x6, w6, h6) - 8) < 1e-12
+    assert abs(oracle.integrate_nd("f64", 3, F["F3_POLY2"], [0, 0, 0, 0, 1, 0], [-1] * 3, [1] * 3, x6, w6, h6)) < 1e-14
+    assert abs(oracle.integrate_nd("f64", 3, F["F3_X2Y2Z2"], None, [-1] * 3, [1] * 3, x6, w6, h6) - 8 / 27) < 1e-13
+    low, up = [-2.0, -1.0, 0.0], [3.0, 2.0, 4.0]
+    mono = lambda lo, hi, p_: (hi ** (p_ + 1) - lo ** (p_ + 1)) / (p_ + 1)
+    vol = lambda px, py, pz: mono(low[0], up[0], px) * mono(low[1], up[1], py) * mono(low[2], up[2], pz)
+    exact = vol(2, 0, 0) + 2 * vol(0, 1, 0) + 3 * vol(0, 0, 2)
+    assert abs(oracle.integrate_nd("f64", 3, F["F3_POLY2"], [0, 1, 2, 3, 0, 0], low, up, x, w, h) - exact) < 1e-10
+    # adaptive 3D families, test/families_3d.jl:51-70 (max_levels=8 there; 6 is enough and fast here)
+    c3 = oracle.cache_tensor("f64", 3, 5)
+    r = oracle.adaptive_nd("f64", 3, F["F3_EXP"], None, [-1] * 3, [1] * 3, 1e-9, 0.0, 5, c3)
+    assert abs(r.value - (math.e - 1 / math.e) ** 3) < 1e-9
+    r = oracle.adaptive_nd("f64", 3, F["F3_RAT"], None, [-1] * 3, [1] * 3, 1e-6, 0.0, 5, c3)
+    exact_rat = (2 * math.atan(5.0) / 5) * (2 * math.atan(4.0) / 4) * (2 * math.atan(3.0) / 3)
+    assert abs(r.value - exact_rat) < 1e-6
+    # evaluation counts
+    r = oracle.adaptive_nd("f64", 3, F["F3_EXP"], None, [-1] * 3, [1] * 3, 0.0, 0.0, 3, c3)
+    assert r.evals == 35937 and r.level == 3
+    c2 = oracle.cache_tensor("f64", 2, 4)
+    r = oracle.adaptive_nd("f64", 2, F["F2_EXP"], None, [-1] * 2, [1] * 2, 0.0, 0.0, 4, c2)
+    assert r.evals == 4225
+
+
+def test_float32(oracle):
+    # test/runtests.jl:101-110 tolerances for Float32 (10*sqrt(eps))
+    x, w, h = oracle.tanhsinh("f32", 80)
+    v = oracle.integrate1d("f32", F["F1_POLY7"], [0, 0, 3.0], -1, 1, x, w, h)
+    assert abs(v - 2.0) < 10 * math.sqrt(np.finfo(np.float32).eps)
+    c = oracle.cache1d("f32", 12)
+    r = oracle.adaptive1d("f32", F["F1_LOG1MX"], None, -1.0, 1.0, 1e-5, 0.0, 12, c)
+    assert abs(r.value - (2 * math.log(2) - 2)) < 1e-4
+
+
+def test_2d_complement_extension_matches_separable_product(oracle):
+    """Config C integrand 1/sqrt((b-x)(y-c)): the tensor-complement oracle equals the analytic
+    4*sqrt((b-a)(d-c)) and the product of two reference-1D complement integrals."""
+    c2 = oracle.cache_tensor_cmpl("f64", 6)
+    c1 = oracle.cache1d("f64", 16, complement=True)
+    a, b, c, d = -2.0, 1.5, -1.25, 2.0
+    r = oracle.adaptive2d_cmpl("f64", F["C2_INVSQRT_BMX_YMC"], None, [a, c], [b, d], 1e-10, 0.0, 6, c2)
+    exact = 4 * math.sqrt((b - a) * (d - c))
+    assert abs(r.value - exact) < 1e-9 * exact
+    # 1D factors: int 1/sqrt(b-x) dx = 2 sqrt(b-a) via C1 family p0/sqrt(bmx*xma) is not separable;
+    # use log-free check through the all-endpoint family instead: product of two pi's
+    r = oracle.adaptive2d_cmpl("f64", F["C2_INVSQRT_ALL"], None, [a, c], [b, d], 1e-10, 0.0, 6, c2)
+    r1 = oracle.adaptive1d_cmpl("f64", F["C1_INVSQRT"], [1.0], a, b, 1e-12, 0.0, 16, c1)
+    r2 = oracle.adaptive1d_cmpl("f64", F["C1_INVSQRT"], [1.0], c, d, 1e-12, 0.0, 16, c1)
+    assert abs(r.value - r1.value * r2.value) < 1e-9 * PI ** 2
+    assert abs(r.value - PI ** 2) < 1e-9 * PI ** 2
+
+
+def test_double64_standin(oracle):
+    """Double64 (__float128 stand-in): quad_cmpl of 1/sqrt(bmx*xma) = pi to 1e-28 (parity unpinned
+    by the reference's own tests; pinned here by the analytic value)."""
+    c = oracle.cache1d("dd", 12, complement=True)
+    one = oracle.q_from_str("1"); m1 = oracle.q_from_str("-1")
+    rtol = oracle.q_from_str("1e-28"); atol = oracle.q_from_str("0")
+    out = oracle.batch_adaptive1d_cmpl_dd(F["C1_INVSQRT"], one, 0, m1, one, 1, rtol, atol, 12, c)
+    s = oracle.q_to_str(out["value"])
+    import mpmath
+    mpmath.mp.dps = 40
+    assert abs(mpmath.mpf(s) - mpmath.pi) < mpmath.mpf("1e-28") * mpmath.pi
+    assert out["converged"][0]
