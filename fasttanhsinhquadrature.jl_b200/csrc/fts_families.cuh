@@ -1,0 +1,222 @@
+// fts_families.cuh — builtin integrand families (one statically compiled sm_100a kernel set each).
+//
+// Formulas are written exactly as the reference's benchmark/test integrands
+// (/root/reference/benchmark/benchmarks.jl:33-45, test/families_{1d,2d,3d}.jl, README.md:102,
+// test/runtests.jl:58-94,246) with Julia's evaluation order; because the library is compiled
+// with --fmad=false nothing is contracted unless written as fma().  `FAST` selects the
+// contracted forms LoopVectorization's @turbo would emit for the `_avx` twins.
+//
+// Functor protocol (also what NVRTC user integrands are wrapped into):
+//   struct F { static constexpr int NP;  template<class T,bool FAST> static T eval(args..., const T* p); }
+#pragma once
+#include "fts_math.cuh"
+
+namespace fts {
+
+template <class F> struct is_cmpl2d;
+
+// Base.pow_body(x, 6) (compensated power by squaring) for Float64; plain products otherwise
+template <class T> __device__ __forceinline__ T jl_pow6(T x)
+{
+    T x2 = x * x;
+    return (x2 * x2) * x2;
+}
+template <> __device__ __forceinline__ double jl_pow6<double>(double x)
+{
+    // n = 6 = 0b110: square, (multiply, square), finish   (Base math.jl pow_body)
+    double x2 = x * x, x2lo = ::fma(x, x, -x2);
+    double err = x2lo;                 // muladd(1, xnlo, x*0)
+    double y = x2, ylo = err;          // two_mul(x2, 1) + err
+    err = x2 * 2 * x2lo;
+    double x4 = x2 * x2, x4lo = ::fma(x2, x2, -x4);
+    x4lo += err;
+    err = ::fma(y, x4lo, x4 * ylo);
+    double r = ::fma(x4, y, err);
+    return (isfinite(x4) && isfinite(err)) ? r : x4 * y;
+}
+template <> __device__ __forceinline__ float jl_pow6<float>(float x)
+{
+    double b = (double)x, b2 = b * b;
+    return (float)((b2 * b2) * b2);
+}
+
+// ---------------------------------------------------------------- 1D: f(x) ------------------
+struct F1Poly7 {
+    static constexpr int NP = 8;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p)
+    {
+        T r = p[7];
+#pragma unroll
+        for (int k = 6; k >= 0; --k) r = muladd<T, FAST>(r, x, p[k]);
+        return r;
+    }
+};
+struct F1Exp {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::exp(x); }
+};
+struct F1Gauss {  // exp(-α*x^2)   README.md:102
+    static constexpr int NP = 1;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p) { return fm::exp(-p[0] * (x * x)); }
+};
+struct F1Runge {  // 1/(1+25x^2)   benchmarks.jl:34
+    static constexpr int NP = 1;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p)
+    {
+        return num<T>::one() / muladd<T, FAST>(p[0], x * x, num<T>::one());
+    }
+};
+struct F1Log1mx {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::log(num<T>::one() - x); }
+};
+struct F1Log1px {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::log(num<T>::one() + x); }
+};
+struct F1InvSqrt1mx2 {  // 1/sqrt(1-x^2)   benchmarks.jl:36
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*)
+    {
+        return num<T>::one() / fm::sqrt(muladd<T, FAST>(-x, x, num<T>::one()));
+    }
+};
+struct F1Sin2 {  // sin(1000x)^2   benchmarks.jl:37
+    static constexpr int NP = 1;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p)
+    {
+        T s = fm::sin(p[0] * x);
+        return s * s;
+    }
+};
+template <> __device__ __forceinline__ dd F1Sin2::eval<dd, false>(dd x, const dd* p) { double s = ::sin((p[0] * x).hi); return dd(s * s); }
+template <> __device__ __forceinline__ dd F1Sin2::eval<dd, true>(dd x, const dd* p) { double s = ::sin((p[0] * x).hi); return dd(s * s); }
+struct F1Poly6 {  // x^6 - 2x^3 + 0.5   benchmarks.jl:33
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*)
+    {
+        return jl_pow6<T>(x) - num<T>::from_double(2.0) * (x * x * x) + num<T>::half();
+    }
+};
+struct F1InvSqrtAbs {  // c/sqrt(|x|)   test/runtests.jl:74
+    static constexpr int NP = 1;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p) { return p[0] / fm::sqrt(fm::abs(x)); }
+};
+
+// ---------------------------------------------------------------- 1D complement: f(x,bmx,xma)
+struct C1InvSqrt {  // c/sqrt(bmx*xma)   test/runtests.jl:82, families_1d.jl:10
+    static constexpr int NP = 1;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T xma, const T* p) { return p[0] / fm::sqrt(bmx * xma); }
+};
+struct C1LogBmx {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T, const T*) { return fm::log(bmx); }
+};
+struct C1LogXma {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T xma, const T*) { return fm::log(xma); }
+};
+struct C1ExpInvBmx {  // exp(-1/bmx)   families_1d.jl:41
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T, const T*) { return fm::exp(-num<T>::one() / bmx); }
+};
+struct C1ExpPlus {  // exp(x)+bmx+xma   test/runtests.jl:246
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T bmx, T xma, const T*) { return fm::exp(x) + bmx + xma; }
+};
+
+// ---------------------------------------------------------------- 2D: f(x,y) ----------------
+struct F2Poly2 {
+    static constexpr int NP = 6;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T* p)
+    {
+        return p[0] + p[1] * x + p[2] * y + p[3] * (x * x) + p[4] * (x * y) + p[5] * (y * y);
+    }
+};
+struct F2Exp {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return fm::exp(x + y); }
+};
+struct F2X2pY2 {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return muladd<T, FAST>(x, x, y * y); }
+};
+struct F2InvSqrt {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*)
+    {
+        const T one = num<T>::one();
+        return one / fm::sqrt(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one));
+    }
+};
+struct F2InvSqrtAbs {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return num<T>::one() / fm::sqrt(fm::abs(x * y)); }
+};
+
+// ---------------------------------------------------------------- 2D complement -------------
+struct C2InvSqrtBmxYmc {  // 1/sqrt((b-x)(y-c))   BASELINE config C
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T bmx, T, T, T ymc, const T*)
+    {
+        return num<T>::one() / fm::sqrt(bmx * ymc);
+    }
+};
+struct C2InvSqrtAll {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T bmx, T xma, T dmy, T ymc, const T*)
+    {
+        return num<T>::one() / fm::sqrt(bmx * xma * dmy * ymc);
+    }
+};
+
+template <> struct is_cmpl2d<C2InvSqrtBmxYmc> { static constexpr bool value = true; };
+template <> struct is_cmpl2d<C2InvSqrtAll> { static constexpr bool value = true; };
+
+// ---------------------------------------------------------------- 3D: f(x,y,z) --------------
+struct F3Poly2 {
+    static constexpr int NP = 6;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T* p)
+    {
+        return p[0] + p[1] * (x * x) + p[2] * y + p[3] * (z * z) + p[4] * (x * y * z) + p[5] * ((x * x) * (y * y) * (z * z));
+    }
+};
+struct F3Exp {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return fm::exp(x + y + z); }
+};
+struct F3X2Y2Z2 {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return (x * x) * (y * y) * (z * z); }
+};
+struct F3InvSqrt {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*)
+    {
+        const T one = num<T>::one();
+        return one / fm::sqrt(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one) * muladd<T, FAST>(-z, z, one));
+    }
+};
+struct F3Rat {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*)
+    {
+        const T one = num<T>::one();
+        return one / (muladd<T, FAST>(num<T>::from_double(25.0), x * x, one) * muladd<T, FAST>(num<T>::from_double(16.0), y * y, one) *
+                      muladd<T, FAST>(num<T>::from_double(9.0), z * z, one));
+    }
+};
+struct F3Log {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*)
+    {
+        const T one = num<T>::one();
+        return fm::log(one - x) * fm::log(one - y) * fm::log(one - z);
+    }
+};
+struct F3InvSqrtAbs {
+    static constexpr int NP = 0;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return num<T>::one() / fm::sqrt(fm::abs(x * y * z)); }
+};
+
+}  // namespace fts

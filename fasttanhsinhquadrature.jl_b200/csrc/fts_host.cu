@@ -1,0 +1,894 @@
+// fts_host.cu — the C ABI of libfts_b200.so (include/fts_b200.h): lifecycle, table/cache handles,
+// kernel registry and launch dispatch.  There is NO CPU fallback: every compute entry point
+// requires an sm_100 device and fails with FTS_ERR_NO_DEVICE / FTS_ERR_CUDA otherwise.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fts_internal.h"
+#include "fts_kernels_cta.cuh"
+
+using namespace fts_host;
+
+// tablegen (fts_tablegen.cpp)
+extern "C" {
+int fts_tg_window(int dtype, int which, int D, void* out);
+int fts_tg_fixed(int dtype, int N, int D, void* x, void* w, void* h);
+int fts_tg_cache1d(int dtype, int L, int complement, void* tm, void* ix, void* iw, void* ic, void* xs, void* ws, void* cs);
+int fts_tg_cache_tensor(int dtype, int D, int L, void* tm, void* ix, void* iw, void* xs, void* ws);
+int fts_tg_tensor_complements(int dtype, int L, const void* tm_in, void* ix, void* iw, void* ic, void* xs, void* ws, void* cs);
+}
+
+// ------------------------------------------------------------------------------- errors ------
+namespace {
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+std::mutex g_mu;
+bool g_inited = false;
+int g_device = -1;
+cudaDeviceProp g_prop;
+cudaStream_t g_stream = nullptr;  // internal stream of the host-buffer entry points
+
+std::vector<KernelEntry>& registry()
+{
+    static std::vector<KernelEntry> r;
+    return r;
+}
+
+const FamilyInfo k_families[] = {
+    {FTS_F1_POLY7, FTS_KIND_1D, 8, "poly7"},
+    {FTS_F1_EXP, FTS_KIND_1D, 0, "exp"},
+    {FTS_F1_GAUSS, FTS_KIND_1D, 1, "gauss"},
+    {FTS_F1_RUNGE, FTS_KIND_1D, 1, "runge"},
+    {FTS_F1_LOG1MX, FTS_KIND_1D, 0, "log1mx"},
+    {FTS_F1_LOG1PX, FTS_KIND_1D, 0, "log1px"},
+    {FTS_F1_INVSQRT1MX2, FTS_KIND_1D, 0, "invsqrt1mx2"},
+    {FTS_F1_SIN2, FTS_KIND_1D, 1, "sin2"},
+    {FTS_F1_POLY6, FTS_KIND_1D, 0, "poly6"},
+    {FTS_F1_INVSQRTABS, FTS_KIND_1D, 1, "invsqrtabs"},
+    {FTS_C1_INVSQRT, FTS_KIND_1D_CMPL, 1, "c_invsqrt"},
+    {FTS_C1_LOG_BMX, FTS_KIND_1D_CMPL, 0, "c_log_bmx"},
+    {FTS_C1_LOG_XMA, FTS_KIND_1D_CMPL, 0, "c_log_xma"},
+    {FTS_C1_EXP_INV_BMX, FTS_KIND_1D_CMPL, 0, "c_exp_inv_bmx"},
+    {FTS_C1_EXP_PLUS, FTS_KIND_1D_CMPL, 0, "c_exp_plus"},
+    {FTS_F2_POLY2, FTS_KIND_2D, 6, "poly2_2d"},
+    {FTS_F2_EXP, FTS_KIND_2D, 0, "exp_2d"},
+    {FTS_F2_X2PY2, FTS_KIND_2D, 0, "x2py2"},
+    {FTS_F2_INVSQRT, FTS_KIND_2D, 0, "invsqrt_2d"},
+    {FTS_F2_INVSQRTABS, FTS_KIND_2D, 0, "invsqrtabs_2d"},
+    {FTS_C2_INVSQRT_BMX_YMC, FTS_KIND_2D_CMPL, 0, "c2_invsqrt_bmx_ymc"},
+    {FTS_C2_INVSQRT_ALL, FTS_KIND_2D_CMPL, 0, "c2_invsqrt_all"},
+    {FTS_F3_POLY2, FTS_KIND_3D, 6, "poly2_3d"},
+    {FTS_F3_EXP, FTS_KIND_3D, 0, "exp_3d"},
+    {FTS_F3_X2Y2Z2, FTS_KIND_3D, 0, "x2y2z2"},
+    {FTS_F3_INVSQRT, FTS_KIND_3D, 0, "invsqrt_3d"},
+    {FTS_F3_RAT, FTS_KIND_3D, 0, "rat_3d"},
+    {FTS_F3_LOG, FTS_KIND_3D, 0, "log_3d"},
+    {FTS_F3_INVSQRTABS, FTS_KIND_3D, 0, "invsqrtabs_3d"},
+};
+
+int kind_dim(int kind)
+{
+    switch (kind) {
+    case FTS_KIND_1D: case FTS_KIND_1D_CMPL: return 1;
+    case FTS_KIND_2D: case FTS_KIND_2D_CMPL: return 2;
+    case FTS_KIND_3D: return 3;
+    }
+    return 0;
+}
+bool kind_cmpl(int kind) { return kind == FTS_KIND_1D_CMPL || kind == FTS_KIND_2D_CMPL; }
+
+// grow-only device scratch slots for the host-buffer entry points
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+enum { S_LOW, S_UP, S_PAR, S_VAL, S_ERR, S_LVL, S_FLG, S_COUNT };
+Scratch g_scratch[S_COUNT];
+}  // namespace
+
+namespace fts_host {
+int set_error(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+int cuda_error(cudaError_t e, const char* what)
+{
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? FTS_ERR_NO_DEVICE : FTS_ERR_CUDA;
+}
+void register_kernels(const KernelEntry* entries, int count)
+{
+    auto& r = registry();
+    r.insert(r.end(), entries, entries + count);
+}
+const void* find_kernel(int family, int dtype, int kid, int fast)
+{
+    for (const auto& e : registry())
+        if (e.family == family && e.dtype == dtype && e.kid == kid && e.fast == fast) return e.fn;
+    return nullptr;
+}
+const FamilyInfo* family_info(int family)
+{
+    for (const auto& f : k_families)
+        if (f.family == family) return &f;
+    return nullptr;
+}
+}  // namespace fts_host
+
+static int ensure_init()
+{
+    if (g_inited) return FTS_OK;
+    return fts_init(-1);
+}
+
+// ------------------------------------------------------------------------------- lifecycle ---
+extern "C" int fts_abi_version(void) { return FTS_ABI_VERSION; }
+
+extern "C" size_t fts_last_error(char* buf, size_t len)
+{
+    if (buf && len) {
+        size_t n = g_last_error.size() < len - 1 ? g_last_error.size() : len - 1;
+        memcpy(buf, g_last_error.data(), n);
+        buf[n] = 0;
+    }
+    return g_last_error.size();
+}
+
+extern "C" int fts_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(FTS_ERR_NO_DEVICE,
+                         "fts_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback");
+    }
+    if (device < 0) {
+        if (g_inited) return FTS_OK;
+        FTS_CUDA(cudaGetDevice(&device));
+    }
+    if (device >= count) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_init: device index out of range");
+    FTS_CUDA(cudaSetDevice(device));
+    FTS_CUDA(cudaGetDeviceProperties(&g_prop, device));
+    if (g_prop.major != 10)
+        return set_error(FTS_ERR_NO_DEVICE, std::string("fts_b200 kernels are built for sm_100a only; device is ") + g_prop.name);
+    if (g_inited && g_device != device) {
+        // re-binding: drop per-device scratch
+        for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+        if (g_stream) cudaStreamDestroy(g_stream);
+        g_stream = nullptr;
+    }
+    if (!g_stream) FTS_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device = device;
+    g_inited = true;
+    return FTS_OK;
+}
+
+extern "C" int fts_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_inited) return FTS_OK;
+    for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+    if (g_stream) cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+    g_inited = false;
+    return FTS_OK;
+}
+
+extern "C" int fts_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, size_t* global_mem)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (device) *device = g_device;
+    if (sm_count) *sm_count = g_prop.multiProcessorCount;
+    if (cc_major) *cc_major = g_prop.major;
+    if (cc_minor) *cc_minor = g_prop.minor;
+    if (global_mem) *global_mem = g_prop.totalGlobalMem;
+    return FTS_OK;
+}
+
+extern "C" int fts_host_alloc(void** ptr, size_t bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    FTS_CUDA(cudaMallocHost(ptr, bytes));
+    return FTS_OK;
+}
+extern "C" int fts_host_free(void* ptr)
+{
+    FTS_CUDA(cudaFreeHost(ptr));
+    return FTS_OK;
+}
+
+extern "C" int64_t fts_launch_count(int reset)
+{
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+extern "C" int fts_family_info(int family, int* kind, int* nparams)
+{
+    const FamilyInfo* f = family_info(family);
+    if (!f) return set_error(FTS_ERR_INVALID_ARGUMENT, "unknown builtin family id");
+    if (kind) *kind = f->kind;
+    if (nparams) *nparams = f->nparams;
+    return FTS_OK;
+}
+
+extern "C" int64_t fts_evals_for_level(int D, int level)
+{
+    // cumulative evaluations (2n+1)^D with n = 2^(level+1)
+    int64_t m = (int64_t(2) << (level + 1)) + 1;
+    return D == 1 ? m : (D == 2 ? m * m : m * m * m);
+}
+extern "C" int64_t fts_evals_fixed(int D, int n)
+{
+    int64_t m = 2 * int64_t(n) + 1;
+    return D == 1 ? m : (D == 2 ? m * m : m * m * m);
+}
+
+// ------------------------------------------------------------------------------- tablegen ----
+static int check_dtype(int dtype)
+{
+    if (dtype != FTS_F32 && dtype != FTS_F64 && dtype != FTS_DD64) return set_error(FTS_ERR_INVALID_ARGUMENT, "unknown dtype");
+    return FTS_OK;
+}
+
+extern "C" int fts_window(int dtype, int which, int D, void* tm_out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (D < 1 || which < 0 || which > 2 || !tm_out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_window: bad arguments");
+    return fts_tg_window(dtype, which, D, tm_out) ? set_error(FTS_ERR_INTERNAL, "fts_window failed") : FTS_OK;
+}
+extern "C" int fts_tanhsinh(int dtype, int N, int D, void* x_out, void* w_out, void* h_out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (N < 2 || D < 1) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_tanhsinh: N must be >= 2 and D >= 1");
+    return fts_tg_fixed(dtype, N, D, x_out, w_out, h_out) ? set_error(FTS_ERR_INTERNAL, "fts_tanhsinh failed") : FTS_OK;
+}
+extern "C" int fts_cache1d_generate(int dtype, int max_levels, int complement, void* tm_out, void* initial_x, void* initial_w,
+                                    void* initial_c, void* xs_flat, void* ws_flat, void* cs_flat)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (max_levels < 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "`max_levels` must be nonnegative.");  // caches.jl:60
+    if (max_levels > 28) return set_error(FTS_ERR_INVALID_ARGUMENT, "max_levels > 28 is not supported");
+    return fts_tg_cache1d(dtype, max_levels, complement, tm_out, initial_x, initial_w, initial_c, xs_flat, ws_flat, cs_flat)
+               ? set_error(FTS_ERR_INTERNAL, "cache generation failed") : FTS_OK;
+}
+extern "C" int fts_cache_tensor_generate(int dtype, int D, int max_levels, void* tm_out, void* initial_x, void* initial_w,
+                                         void* xs_flat, void* ws_flat)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (max_levels < 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "`max_levels` must be nonnegative.");  // caches.jl:149
+    if (D != 2 && D != 3) return set_error(FTS_ERR_INVALID_ARGUMENT, "tensor caches exist for D = 2, 3");
+    if (max_levels > 24) return set_error(FTS_ERR_INVALID_ARGUMENT, "max_levels > 24 is not supported");
+    return fts_tg_cache_tensor(dtype, D, max_levels, tm_out, initial_x, initial_w, xs_flat, ws_flat)
+               ? set_error(FTS_ERR_INTERNAL, "cache generation failed") : FTS_OK;
+}
+extern "C" int fts_cache_tensor_cmpl_generate(int dtype, int max_levels, void* tm_out, void* initial_x, void* initial_w,
+                                              void* initial_c, void* xs_flat, void* ws_flat, void* cs_flat)
+{
+    if (dtype != FTS_F32 && dtype != FTS_F64) return set_error(FTS_ERR_UNSUPPORTED, "2D complement tables: f32/f64 only");
+    if (max_levels < 0 || max_levels > 24) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad max_levels");
+    // window t_w_max(T, 2): products of two weights/complements stay above floatmin (core.jl:207-221)
+    unsigned char tm[16];
+    fts_tg_window(dtype, 2, 2, tm);
+    memcpy(tm_out, tm, dtype_size(dtype));
+    if (fts_tg_tensor_complements(dtype, max_levels, tm, initial_x, initial_w, initial_c, xs_flat, ws_flat, cs_flat))
+        return set_error(FTS_ERR_INTERNAL, "tensor complement table generation failed");
+    return FTS_OK;
+}
+
+// ------------------------------------------------------------------------------- uploads -----
+template <class T>
+static int upload_nodes(const T* x, const T* w, const T* c, long long count, void** d_nodes, void** d_nodes_c)
+{
+    *d_nodes = nullptr;
+    *d_nodes_c = nullptr;
+    if (count == 0) return FTS_OK;
+    std::vector<fts::Node<T>> h(count);
+    for (long long i = 0; i < count; ++i) { h[i].x = x[i]; h[i].w = w[i]; }
+    FTS_CUDA(cudaMalloc(d_nodes, sizeof(fts::Node<T>) * count));
+    FTS_CUDA(cudaMemcpy(*d_nodes, h.data(), sizeof(fts::Node<T>) * count, cudaMemcpyHostToDevice));
+    if (c) {
+        std::vector<fts::NodeC<T>> hc(count);
+        for (long long i = 0; i < count; ++i) { hc[i].x = x[i]; hc[i].w = w[i]; hc[i].c = c[i]; hc[i].pad = T(0.0); }
+        FTS_CUDA(cudaMalloc(d_nodes_c, sizeof(fts::NodeC<T>) * count));
+        FTS_CUDA(cudaMemcpy(*d_nodes_c, hc.data(), sizeof(fts::NodeC<T>) * count, cudaMemcpyHostToDevice));
+    }
+    return FTS_OK;
+}
+
+static int upload_nodes_any(int dtype, const void* x, const void* w, const void* c, long long count, void** dn, void** dc)
+{
+    switch (dtype) {
+    case FTS_F32: return upload_nodes<float>((const float*)x, (const float*)w, (const float*)c, count, dn, dc);
+    case FTS_F64: return upload_nodes<double>((const double*)x, (const double*)w, (const double*)c, count, dn, dc);
+    case FTS_DD64: return upload_nodes<fts::dd>((const fts::dd*)x, (const fts::dd*)w, (const fts::dd*)c, count, dn, dc);
+    }
+    return set_error(FTS_ERR_INVALID_ARGUMENT, "unknown dtype");
+}
+
+extern "C" int fts_tables_fixed_upload(int dtype, int n, const void* x, const void* w, const void* h, fts_tables* out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (n < 0 || !x || !w || !h || !out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_tables_fixed_upload: bad arguments");
+    if (int rc = ensure_init()) return rc;
+    fts_tables_s* t = new fts_tables_s();
+    t->dtype = dtype;
+    t->n = n;
+    memset(t->h, 0, sizeof t->h);
+    memcpy(t->h, h, dtype_size(dtype));
+    void* dummy = nullptr;
+    int rc = upload_nodes_any(dtype, x, w, nullptr, n, &t->d_grid, &dummy);
+    if (rc) { delete t; return rc; }
+    *out = t;
+    return FTS_OK;
+}
+extern "C" int fts_tables_free(fts_tables t)
+{
+    if (!t) return FTS_OK;
+    if (t->d_grid) cudaFree(t->d_grid);
+    delete t;
+    return FTS_OK;
+}
+
+static int make_cache(int dtype, int D, int kind, int max_levels, const void* tm, const void* ix, const void* iw, const void* ic,
+                      const void* xs, const void* ws, const void* cs, fts_cache* out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (max_levels < 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "`max_levels` must be nonnegative.");
+    if (!tm || !ix || !iw || !out || (max_levels > 0 && (!xs || !ws))) return set_error(FTS_ERR_INVALID_ARGUMENT, "cache upload: null argument");
+    if (kind == 1 && (!ic || (max_levels > 0 && !cs))) return set_error(FTS_ERR_INVALID_ARGUMENT, "complement cache upload needs initial_c and cs");
+    if (int rc = ensure_init()) return rc;
+    const size_t es = dtype_size(dtype);
+    fts_cache_s* c = new fts_cache_s();
+    c->dtype = dtype; c->D = D; c->kind = kind; c->max_levels = max_levels;
+    c->count = D == 0 ? ((2LL << max_levels) - 2) : ((4LL << max_levels) - 4);
+    memset(c->tm, 0, sizeof c->tm); memset(c->ix, 0, sizeof c->ix); memset(c->iw, 0, sizeof c->iw); memset(c->ic, 0, sizeof c->ic);
+    memcpy(c->tm, tm, es); memcpy(c->ix, ix, 2 * es); memcpy(c->iw, iw, 2 * es);
+    if (ic) memcpy(c->ic, ic, 2 * es);
+    int rc = upload_nodes_any(dtype, xs, ws, kind == 1 ? cs : nullptr, c->count, &c->d_nodes, &c->d_nodes_c);
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return FTS_OK;
+}
+
+extern "C" int fts_cache1d_upload(int dtype, int kind, int max_levels, const void* tm, const void* initial_x, const void* initial_w,
+                                  const void* initial_c, const void* xs_flat, const void* ws_flat, const void* cs_flat, fts_cache* out)
+{
+    if (kind != 0 && kind != 1) return set_error(FTS_ERR_INVALID_ARGUMENT, "cache kind must be 0 (regular) or 1 (complement)");
+    return make_cache(dtype, 0, kind, max_levels, tm, initial_x, initial_w, initial_c, xs_flat, ws_flat, cs_flat, out);
+}
+extern "C" int fts_cache_tensor_upload(int dtype, int D, int max_levels, const void* tm, const void* initial_x, const void* initial_w,
+                                       const void* xs_flat, const void* ws_flat, fts_cache* out)
+{
+    if (D != 2 && D != 3) return set_error(FTS_ERR_INVALID_ARGUMENT, "tensor caches exist for D = 2, 3");
+    return make_cache(dtype, D, 0, max_levels, tm, initial_x, initial_w, nullptr, xs_flat, ws_flat, nullptr, out);
+}
+extern "C" int fts_cache_tensor_cmpl_upload(int dtype, int max_levels, const void* tm, const void* initial_x, const void* initial_w,
+                                            const void* initial_c, const void* xs_flat, const void* ws_flat, const void* cs_flat, fts_cache* out)
+{
+    return make_cache(dtype, 2, 1, max_levels, tm, initial_x, initial_w, initial_c, xs_flat, ws_flat, cs_flat, out);
+}
+extern "C" int fts_cache_info(fts_cache c, int* dtype, int* D, int* kind, int* max_levels)
+{
+    if (!c) return set_error(FTS_ERR_INVALID_ARGUMENT, "null cache");
+    if (dtype) *dtype = c->dtype;
+    if (D) *D = c->D;
+    if (kind) *kind = c->kind;
+    if (max_levels) *max_levels = c->max_levels;
+    return FTS_OK;
+}
+extern "C" int fts_cache_free(fts_cache c)
+{
+    if (!c) return FTS_OK;
+    if (c->d_nodes) cudaFree(c->d_nodes);
+    if (c->d_nodes_c) cudaFree(c->d_nodes_c);
+    delete c;
+    return FTS_OK;
+}
+
+// ------------------------------------------------------------------------------- integrands --
+extern "C" int fts_integrand_builtin(int family, fts_integrand* out)
+{
+    const FamilyInfo* fi = family_info(family);
+    if (!fi || !out) return set_error(FTS_ERR_INVALID_ARGUMENT, "unknown builtin family id");
+    fts_integrand_s* f = new fts_integrand_s();
+    f->builtin = 1; f->family = family; f->kind = fi->kind; f->nparams = fi->nparams;
+    f->module = nullptr;
+    *out = f;
+    return FTS_OK;
+}
+extern "C" int fts_integrand_info(fts_integrand f, int* kind, int* nparams, int* is_builtin)
+{
+    if (!f) return set_error(FTS_ERR_INVALID_ARGUMENT, "null integrand");
+    if (kind) *kind = f->kind;
+    if (nparams) *nparams = f->nparams;
+    if (is_builtin) *is_builtin = f->builtin;
+    return FTS_OK;
+}
+extern "C" int fts_integrand_free(fts_integrand f)
+{
+    delete f;  // NVRTC modules stay in the process-wide compile cache
+    return FTS_OK;
+}
+
+static const void* integrand_kernel(fts_integrand f, int dtype, int kid, int fast)
+{
+    if (f->builtin) return find_kernel(f->family, dtype, kid, fast);
+    return fts_nvrtc_kernel(f->module, dtype, kid, fast);
+}
+
+// ------------------------------------------------------------------------------- launches ----
+template <class T> static T load_elem(const void* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+static double elem_hi(int dtype, const void* p) { return dtype == FTS_F32 ? (double)load_elem<float>(p) : load_elem<double>(p); }
+
+static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, void* args, cudaStream_t s)
+{
+    if (smem > 48 * 1024) {
+        if (smem > (size_t)g_prop.sharedMemPerBlockOptin)
+            return set_error(FTS_ERR_UNSUPPORTED, "level needs " + std::to_string(smem) + " B of shared memory per CTA (max " +
+                                                      std::to_string(g_prop.sharedMemPerBlockOptin) + ")");
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            FTS_CUDA(cudaKernelSetAttributeForDevice((cudaKernel_t)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, g_device));
+        }
+    }
+    void* params[] = {args};
+    FTS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(block), params, smem, s));
+    g_launches.fetch_add(1);
+    return FTS_OK;
+}
+
+static int launch(const void* fn, long long threads, int block, void* args, cudaStream_t s)
+{
+    if (threads <= 0) return FTS_OK;
+    long long blocks = (threads + block - 1) / block;
+    if (blocks > 0x7fffffffLL) return set_error(FTS_ERR_INVALID_ARGUMENT, "batch too large for one launch");
+    return launch_raw(fn, (unsigned)blocks, block, 0, args, s);
+}
+
+// Which kernel style serves a launch.  Thread-per-integral needs enough integrals
+// to fill 148 SMs; below that one CTA per integral; below ~2 CTAs per SM and with deep levels
+// (2D/3D) one whole-grid launch per level.
+enum Style { STYLE_TPI, STYLE_CTA, STYLE_GRID };
+static Style pick_style(int order, int dim, long long batch, int max_levels, bool have_cta, bool have_grid)
+{
+    if (order == FTS_ORDER_REFERENCE) return STYLE_TPI;
+    const long long sms = g_prop.multiProcessorCount;
+    const long long tpi_min = dim == 1 ? 32 * sms : 64 * sms;  // >= 4.7k / 9.5k integrals
+    if (order == FTS_ORDER_AUTO && batch >= tpi_min) return STYLE_TPI;
+    if (order == FTS_ORDER_FAST && batch >= 8 * tpi_min) return STYLE_TPI;
+    if (dim >= 2 && have_grid && batch < 2 * sms && max_levels >= (dim == 3 ? 4 : 7)) return STYLE_GRID;
+    return have_cta ? STYLE_CTA : STYLE_TPI;
+}
+
+template <class T> static void fill_cache_args(fts::Args<T>& a, fts_cache c)
+{
+    a.nodes = (const fts::Node<T>*)c->d_nodes;
+    a.nodes_c = (const fts::NodeC<T>*)c->d_nodes_c;
+    a.tm = load_elem<T>(c->tm);
+    for (int i = 0; i < 2; ++i) {
+        a.ix[i] = load_elem<T>(c->ix + i * sizeof(T));
+        a.iw[i] = load_elem<T>(c->iw + i * sizeof(T));
+        a.ic[i] = load_elem<T>(c->ic + i * sizeof(T));
+    }
+}
+
+template <class T>
+static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bstride, const void* params,
+                     int pstride, long long batch, void* out_value, cudaStream_t s)
+{
+    const int dim = kind_dim(f->kind);
+    const void* fn_cta = t->dtype == FTS_DD64 ? nullptr : integrand_kernel(f, t->dtype, KID_FIXED_CTA, 1);
+    const size_t smem = dim == 1 ? 0 : (size_t)(dim == 2 ? 5 : 7) * t->n * sizeof(T);
+    const bool cta_ok = fn_cta && smem <= (size_t)g_prop.sharedMemPerBlockOptin;
+    Style st = pick_style(order, dim, batch, 0, cta_ok, false);
+    fts::Args<T> a;
+    memset(&a, 0, sizeof a);
+    a.grid = (const fts::Node<T>*)t->d_grid;
+    a.n = t->n;
+    a.h = load_elem<T>(t->h);
+    a.low = (const T*)low; a.up = (const T*)up; a.bstride = bstride;
+    a.params = (const T*)params; a.pstride = pstride;
+    a.batch = batch;
+    a.value = (T*)out_value;
+    if (batch == 0) return FTS_OK;
+    if (st == STYLE_CTA) return launch_raw(fn_cta, (unsigned)batch, fts::CTA_THREADS, smem, &a, s);
+    const int fast = order == FTS_ORDER_REFERENCE ? 0 : (order == FTS_ORDER_FAST ? 1 : 0);
+    const void* fn = integrand_kernel(f, t->dtype, KID_FIXED_TPI, fast);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no fixed-grid kernel built for this integrand/dtype/order");
+    return launch(fn, batch, dim == 1 ? 256 : 128, &a, s);
+}
+
+static int check_fixed(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bstride, const void* params,
+                       int pstride, long long batch, void* out_value)
+{
+    if (!t || !f) return set_error(FTS_ERR_INVALID_ARGUMENT, "null handle");
+    if (kind_cmpl(f->kind)) return set_error(FTS_ERR_UNSUPPORTED, "fixed-grid complement integration is not on the reference's exported path");
+    const int dim = kind_dim(f->kind);
+    if (bstride != 0 && bstride != dim) return set_error(FTS_ERR_DIMENSION_MISMATCH, "low/up must have length " + std::to_string(dim) + " per integral");
+    if (f->nparams > 0 && (!params || (pstride != 0 && pstride < f->nparams))) return set_error(FTS_ERR_INVALID_ARGUMENT, "integrand needs " + std::to_string(f->nparams) + " parameters per integral");
+    if (batch < 0 || !low || !up || (batch > 0 && !out_value)) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    if (order != FTS_ORDER_REFERENCE && order != FTS_ORDER_FAST && order != FTS_ORDER_AUTO) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad order");
+    return ensure_init();
+}
+
+extern "C" int fts_integrate_batch_dev(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bounds_stride,
+                                       const void* params, int params_stride, int64_t batch, void* out_value, void* stream)
+{
+    if (int rc = check_fixed(t, f, order, low, up, bounds_stride, params, params_stride, batch, out_value)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (t->dtype) {
+    case FTS_F32: return run_fixed<float>(t, f, order, low, up, bounds_stride, params, params_stride, batch, out_value, s);
+    case FTS_F64: return run_fixed<double>(t, f, order, low, up, bounds_stride, params, params_stride, batch, out_value, s);
+    case FTS_DD64: return run_fixed<fts::dd>(t, f, order, low, up, bounds_stride, params, params_stride, batch, out_value, s);
+    }
+    return set_error(FTS_ERR_INTERNAL, "bad dtype");
+}
+
+// host <-> device staging for the host-buffer entry points
+static int stage_in(int slot, const void* host, size_t bytes, void** dev)
+{
+    *dev = nullptr;
+    if (!host || bytes == 0) return FTS_OK;
+    FTS_CUDA(g_scratch[slot].need(bytes));
+    FTS_CUDA(cudaMemcpyAsync(g_scratch[slot].p, host, bytes, cudaMemcpyHostToDevice, g_stream));
+    *dev = g_scratch[slot].p;
+    return FTS_OK;
+}
+static int stage_out(int slot, bool wanted, size_t bytes, void** dev)
+{
+    *dev = nullptr;
+    if (!wanted || bytes == 0) return FTS_OK;
+    FTS_CUDA(g_scratch[slot].need(bytes));
+    *dev = g_scratch[slot].p;
+    return FTS_OK;
+}
+
+extern "C" int fts_integrate_batch(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bounds_stride,
+                                   const void* params, int params_stride, int64_t batch, void* out_value)
+{
+    if (int rc = check_fixed(t, f, order, low, up, bounds_stride, params, params_stride, batch, out_value)) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t es = dtype_size(t->dtype);
+    const int dim = kind_dim(f->kind);
+    const size_t nb = bounds_stride ? (size_t)batch * bounds_stride : (size_t)dim;
+    const size_t np = f->nparams ? (params_stride ? (size_t)batch * params_stride : (size_t)f->nparams) : 0;
+    void *dl, *du, *dp, *dv;
+    if (int rc = stage_in(S_LOW, low, nb * es, &dl)) return rc;
+    if (int rc = stage_in(S_UP, up, nb * es, &du)) return rc;
+    if (int rc = stage_in(S_PAR, params, np * es, &dp)) return rc;
+    if (int rc = stage_out(S_VAL, true, (size_t)batch * es, &dv)) return rc;
+    if (int rc = fts_integrate_batch_dev(t, f, order, dl, du, bounds_stride, dp, params_stride, batch, dv, g_stream)) return rc;
+    if (batch) FTS_CUDA(cudaMemcpyAsync(out_value, dv, (size_t)batch * es, cudaMemcpyDeviceToHost, g_stream));
+    FTS_CUDA(cudaStreamSynchronize(g_stream));
+    return FTS_OK;
+}
+
+// ---- whole-grid level machinery (one large 2D/3D integral; also the multi-GPU shard path) ----
+template <class T, int D>
+__global__ void k_state_to_result(const T* state, const T* low, const T* up, int max_levels, int options, T* value, T* err, int* levels, int* flags)
+{
+    const int done = (int)fts::num<T>::to_double(state[5]);
+    int fl = done == 2 ? (fts::FLAG_ZERO_WIDTH | fts::FLAG_CONVERGED) : (done == 1 ? fts::FLAG_CONVERGED : (max_levels > 0 ? fts::FLAG_MAX_LEVELS : 0));
+    if (options & fts::OPT_QUAD_EDGE) {  // flipped bounds give the negated value through the signed half-widths
+        bool neg = false;
+        for (int d = 0; d < D; ++d) neg = neg != (low[d] > up[d]);
+        if (neg) fl |= fts::FLAG_FLIPPED;
+    }
+    *value = state[3];
+    if (err) *err = state[4];
+    if (levels) *levels = (int)fts::num<T>::to_double(state[6]);
+    if (flags) *flags = fl;
+}
+
+static size_t grid_level_smem(int dim, bool cmpl, int level, size_t es)
+{
+    const size_t n = level == 0 ? 2 : ((size_t)2 << level);
+    return (dim == 3 ? 7 : (cmpl ? 9 : 5)) * n * es;
+}
+
+static unsigned grid_level_blocks(int dim, int level, int nranks)
+{
+    const double n = level == 0 ? 2.0 : (double)(2 << level);
+    const double cells = (dim == 3 ? 0.875 * n * n * n + 0.75 * n * n : 0.75 * n * n + n) / nranks;
+    double want = cells / (fts::CTA_THREADS * 2.0);  // >= 2 cells per thread
+    const double cap = (double)g_prop.multiProcessorCount * 4;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (unsigned)want;
+}
+
+template <class T>
+static int launch_level(const void* fn, fts_cache c, int dim, bool cmpl, const T* low, const T* up, const T* params, int level, int rank,
+                        int nranks, T* block_partials, unsigned int* ticket, T* partial_out, const T* state, cudaStream_t s)
+{
+    fts::Args<T> a;
+    memset(&a, 0, sizeof a);
+    fill_cache_args(a, c);
+    a.low = low; a.up = up; a.params = params; a.bstride = dim; a.pstride = 0; a.batch = 1;
+    a.level = level; a.rank = rank; a.nranks = nranks;
+    a.block_partials = block_partials; a.ticket = ticket; a.partial_out = partial_out; a.state = state;
+    return launch_raw(fn, grid_level_blocks(dim, level, nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s);
+}
+
+template <class T, int D> static void launch_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks, const T* partials, T* state, cudaStream_t s, int options = 0)
+{
+    fts::k_sharded_step<T, D><<<1, 1, 0, s>>>(low, up, tm, rtol, atol, level, nranks, partials, state, options);
+    g_launches.fetch_add(1);
+}
+
+// adaptive integration of a SMALL batch of large 2D/3D integrals: per integral, one whole-grid
+// launch per level + a one-thread stop test, all queued on the stream without host round trips
+// (later levels early-exit once the device-side `done` flag is set).
+template <class T>
+static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int options, const T* low, const T* up, int bstride,
+                             const T* params, int pstride, T rtol, T atol, int max_levels, long long batch, T* out_value, T* out_err,
+                             int32_t* out_levels, int32_t* out_flags, cudaStream_t s)
+{
+    const int dim = kind_dim(f->kind);
+    const bool cmpl = kind_cmpl(f->kind);
+    const size_t nblk = (size_t)g_prop.multiProcessorCount * 4;
+    T* scratch = nullptr;
+    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2 + 8 + 2) * sizeof(T), s));
+    T* block_partials = scratch;
+    T* partial = scratch + 2 * nblk;
+    T* state = partial + 2;
+    unsigned int* ticket = (unsigned int*)(state + 8);
+    FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    const T tm = load_elem<T>(c->tm);
+    for (long long b = 0; b < batch; ++b) {
+        const T* lo = low + b * bstride;
+        const T* hi = up + b * bstride;
+        const T* pp = params ? params + b * pstride : nullptr;
+        for (int level = 0; level <= max_levels; ++level) {
+            if (int rc = launch_level<T>(fn, c, dim, cmpl, lo, hi, pp, level, 0, 1, block_partials, ticket, partial, level ? state : nullptr, s)) return rc;
+            if (dim == 3) launch_step<T, 3>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options);
+            else launch_step<T, 2>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options);
+        }
+        if (dim == 3) k_state_to_result<T, 3><<<1, 1, 0, s>>>(state, lo, hi, max_levels, options, out_value + b, out_err ? out_err + b : nullptr,
+                                                              out_levels ? out_levels + b : nullptr, out_flags ? out_flags + b : nullptr);
+        else k_state_to_result<T, 2><<<1, 1, 0, s>>>(state, lo, hi, max_levels, options, out_value + b, out_err ? out_err + b : nullptr,
+                                                     out_levels ? out_levels + b : nullptr, out_flags ? out_flags + b : nullptr);
+        g_launches.fetch_add(1);
+    }
+    FTS_CUDA(cudaGetLastError());
+    FTS_CUDA(cudaFreeAsync(scratch, s));
+    return FTS_OK;
+}
+
+template <class T>
+static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, const void* low, const void* up, int bstride,
+                        const void* params, int pstride, const void* rtol, const void* atol, int max_levels, long long batch,
+                        void* out_value, void* out_err, int32_t* out_levels, int32_t* out_flags, cudaStream_t s)
+{
+    if (batch == 0) return FTS_OK;
+    const int dim = kind_dim(f->kind);
+    const bool cmpl = kind_cmpl(f->kind);
+    const bool is_dd = c->dtype == FTS_DD64;
+    const void* fn_cta = is_dd ? nullptr : integrand_kernel(f, c->dtype, KID_ADAPT_CTA, 1);
+    const void* fn_grid = (is_dd || dim == 1) ? nullptr : integrand_kernel(f, c->dtype, KID_LEVEL_GRID, 1);
+    const size_t nmax = max_levels > 0 ? ((size_t)2 << max_levels) : 2;
+    const size_t smem_cta = dim == 1 ? 0 : (dim == 3 ? 7 : (cmpl ? 9 : 5)) * nmax * sizeof(T);
+    const bool cta_ok = fn_cta && smem_cta <= (size_t)g_prop.sharedMemPerBlockOptin;
+    const bool grid_ok = fn_grid && grid_level_smem(dim, cmpl, max_levels, sizeof(T)) <= (size_t)g_prop.sharedMemPerBlockOptin;
+    Style st = pick_style(order, dim, batch, max_levels, cta_ok, grid_ok);
+    if (st == STYLE_GRID)
+        return run_adaptive_grid<T>(fn_grid, c, f, options, (const T*)low, (const T*)up, bstride, (const T*)params, pstride, load_elem<T>(rtol),
+                                    load_elem<T>(atol), max_levels, batch, (T*)out_value, (T*)out_err, out_levels, out_flags, s);
+    fts::Args<T> a;
+    memset(&a, 0, sizeof a);
+    fill_cache_args(a, c);
+    a.low = (const T*)low; a.up = (const T*)up; a.bstride = bstride;
+    a.params = (const T*)params; a.pstride = pstride;
+    a.rtol = load_elem<T>(rtol); a.atol = load_elem<T>(atol);
+    a.max_levels = max_levels; a.options = options; a.batch = batch;
+    a.value = (T*)out_value; a.err = (T*)out_err; a.levels = out_levels; a.flags = out_flags;
+    if (st == STYLE_CTA) {
+        if (batch > 0x7fffffffLL) return set_error(FTS_ERR_INVALID_ARGUMENT, "batch too large for one launch");
+        return launch_raw(fn_cta, (unsigned)batch, fts::CTA_THREADS, smem_cta, &a, s);
+    }
+    const int fast = order == FTS_ORDER_FAST ? 1 : 0;
+    const void* fn = integrand_kernel(f, c->dtype, KID_ADAPT_TPI, fast);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no adaptive kernel built for this integrand/dtype/order");
+    return launch(fn, batch, dim == 1 ? 256 : 128, &a, s);
+}
+
+static int check_cache_match(fts_cache c, fts_integrand f)
+{
+    const int dim = kind_dim(f->kind);
+    const int cdim = c->D == 0 ? 1 : c->D;
+    if (dim != cdim) return set_error(FTS_ERR_DIMENSION_MISMATCH, "integrand is " + std::to_string(dim) + "D but the cache is " + std::to_string(cdim) + "D");
+    if (kind_cmpl(f->kind) && c->kind != 1) return set_error(FTS_ERR_INVALID_ARGUMENT, "complement integrands need a complement cache (adaptive_cache_1D(T; complement=true))");
+    return FTS_OK;
+}
+
+static int check_adaptive(fts_cache c, fts_integrand f, int order, const void* low, const void* up, int bstride, const void* params,
+                          int pstride, const void* rtol, const void* atol, int max_levels, long long batch, void* out_value)
+{
+    if (!c || !f) return set_error(FTS_ERR_INVALID_ARGUMENT, "null handle");
+    if (int rc = check_cache_match(c, f)) return rc;
+    const int dim = kind_dim(f->kind);
+    if (max_levels < 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "`max_levels` must be nonnegative.");
+    if (c->max_levels < max_levels)  // caches.jl:25-29
+        return set_error(FTS_ERR_INVALID_ARGUMENT, "provided adaptive cache supports " + std::to_string(c->max_levels) + " levels, but `max_levels=" + std::to_string(max_levels) + "` was requested.");
+    if (!rtol || !atol) return set_error(FTS_ERR_INVALID_ARGUMENT, "rtol/atol pointers are required");
+    if (!(elem_hi(c->dtype, rtol) >= 0.0)) return set_error(FTS_ERR_INVALID_ARGUMENT, "`rtol` must be nonnegative.");  // core.jl:41
+    if (!(elem_hi(c->dtype, atol) >= 0.0)) return set_error(FTS_ERR_INVALID_ARGUMENT, "`atol` must be nonnegative.");  // core.jl:42
+    if (bstride != 0 && bstride != dim) return set_error(FTS_ERR_DIMENSION_MISMATCH, "low/up must have length " + std::to_string(dim) + " per integral");
+    if (f->nparams > 0 && (!params || (pstride != 0 && pstride < f->nparams))) return set_error(FTS_ERR_INVALID_ARGUMENT, "integrand needs " + std::to_string(f->nparams) + " parameters per integral");
+    if (batch < 0 || !low || !up || (batch > 0 && !out_value)) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    if (order != FTS_ORDER_REFERENCE && order != FTS_ORDER_FAST && order != FTS_ORDER_AUTO) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad order");
+    return ensure_init();
+}
+
+extern "C" int fts_adaptive_batch_dev(fts_cache c, fts_integrand f, int order, int options, const void* low, const void* up,
+                                      int bounds_stride, const void* params, int params_stride, const void* rtol, const void* atol,
+                                      int max_levels, int64_t batch, void* out_value, void* out_err, int32_t* out_levels,
+                                      int32_t* out_flags, void* stream)
+{
+    if (int rc = check_adaptive(c, f, order, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (c->dtype) {
+    case FTS_F32: return run_adaptive<float>(c, f, order, options, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value, out_err, out_levels, out_flags, s);
+    case FTS_F64: return run_adaptive<double>(c, f, order, options, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value, out_err, out_levels, out_flags, s);
+    case FTS_DD64: return run_adaptive<fts::dd>(c, f, order, options, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value, out_err, out_levels, out_flags, s);
+    }
+    return set_error(FTS_ERR_INTERNAL, "bad dtype");
+}
+
+extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int options, const void* low, const void* up,
+                                  int bounds_stride, const void* params, int params_stride, const void* rtol, const void* atol,
+                                  int max_levels, int64_t batch, void* out_value, void* out_err, int32_t* out_levels, int32_t* out_flags)
+{
+    if (int rc = check_adaptive(c, f, order, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value)) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t es = dtype_size(c->dtype);
+    const int dim = kind_dim(f->kind);
+    const size_t nb = bounds_stride ? (size_t)batch * bounds_stride : (size_t)dim;
+    const size_t np = f->nparams ? (params_stride ? (size_t)batch * params_stride : (size_t)f->nparams) : 0;
+    void *dl, *du, *dp, *dv, *de, *dlv, *dfl;
+    if (int rc = stage_in(S_LOW, low, nb * es, &dl)) return rc;
+    if (int rc = stage_in(S_UP, up, nb * es, &du)) return rc;
+    if (int rc = stage_in(S_PAR, params, np * es, &dp)) return rc;
+    if (int rc = stage_out(S_VAL, true, (size_t)batch * es, &dv)) return rc;
+    if (int rc = stage_out(S_ERR, out_err != nullptr, (size_t)batch * es, &de)) return rc;
+    if (int rc = stage_out(S_LVL, out_levels != nullptr, (size_t)batch * 4, &dlv)) return rc;
+    if (int rc = stage_out(S_FLG, out_flags != nullptr, (size_t)batch * 4, &dfl)) return rc;
+    if (int rc = fts_adaptive_batch_dev(c, f, order, options, dl, du, bounds_stride, dp, params_stride, rtol, atol, max_levels, batch,
+                                        dv, de, (int32_t*)dlv, (int32_t*)dfl, g_stream))
+        return rc;
+    if (batch) {
+        FTS_CUDA(cudaMemcpyAsync(out_value, dv, (size_t)batch * es, cudaMemcpyDeviceToHost, g_stream));
+        if (out_err) FTS_CUDA(cudaMemcpyAsync(out_err, de, (size_t)batch * es, cudaMemcpyDeviceToHost, g_stream));
+        if (out_levels) FTS_CUDA(cudaMemcpyAsync(out_levels, dlv, (size_t)batch * 4, cudaMemcpyDeviceToHost, g_stream));
+        if (out_flags) FTS_CUDA(cudaMemcpyAsync(out_flags, dfl, (size_t)batch * 4, cudaMemcpyDeviceToHost, g_stream));
+    }
+    FTS_CUDA(cudaStreamSynchronize(g_stream));
+    return FTS_OK;
+}
+
+// ---- sharded single integral (multi-GPU: one process per GPU, exchange by the caller) -----------
+template <class T>
+static int sharded_level(fts_cache c, fts_integrand f, const void* low, const void* up, const void* params, int level, int rank, int nranks,
+                         void* partial_dev, const void* state_dev, cudaStream_t s)
+{
+    const int dim = kind_dim(f->kind);
+    const bool cmpl = kind_cmpl(f->kind);
+    const void* fn = integrand_kernel(f, c->dtype, KID_LEVEL_GRID, 1);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no whole-grid level kernel for this integrand/dtype");
+    const size_t nblk = (size_t)g_prop.multiProcessorCount * 4;
+    T* scratch = nullptr;
+    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2) * sizeof(T), s));
+    unsigned int* ticket = (unsigned int*)(scratch + 2 * nblk);
+    FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    int rc = launch_level<T>(fn, c, dim, cmpl, (const T*)low, (const T*)up, (const T*)params, level, rank, nranks, scratch, ticket,
+                             (T*)partial_dev, level ? (const T*)state_dev : nullptr, s);
+    FTS_CUDA(cudaFreeAsync(scratch, s));
+    return rc;
+}
+
+extern "C" int fts_adaptive_sharded_level_dev(fts_cache c, fts_integrand f, const void* low, const void* up, const void* params, int level,
+                                              int rank, int nranks, void* partial_dev, const void* state_dev, void* stream)
+{
+    if (!c || !f || !low || !up || !partial_dev) return set_error(FTS_ERR_INVALID_ARGUMENT, "sharded level: null argument");
+    if (int rc = check_cache_match(c, f)) return rc;
+    if (kind_dim(f->kind) < 2) return set_error(FTS_ERR_UNSUPPORTED, "outer-axis sharding exists for 2D/3D integrals");
+    if (level < 0 || level > c->max_levels) return set_error(FTS_ERR_INVALID_ARGUMENT, "provided adaptive cache supports " + std::to_string(c->max_levels) + " levels, but `max_levels=" + std::to_string(level) + "` was requested.");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad rank/nranks");
+    if (f->nparams > 0 && !params) return set_error(FTS_ERR_INVALID_ARGUMENT, "integrand needs parameters");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->dtype == FTS_F32) return sharded_level<float>(c, f, low, up, params, level, rank, nranks, partial_dev, state_dev, s);
+    if (c->dtype == FTS_F64) return sharded_level<double>(c, f, low, up, params, level, rank, nranks, partial_dev, state_dev, s);
+    return set_error(FTS_ERR_UNSUPPORTED, "sharded levels: f32/f64 only");
+}
+
+extern "C" int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up, const void* rtol, const void* atol, int level,
+                                             int nranks, const void* partials_dev, void* state_dev, void* stream)
+{
+    if (!c || !low || !up || !rtol || !atol || !partials_dev || !state_dev) return set_error(FTS_ERR_INVALID_ARGUMENT, "sharded step: null argument");
+    if (c->D != 2 && c->D != 3) return set_error(FTS_ERR_UNSUPPORTED, "sharded step needs a tensor cache");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->dtype == FTS_F64) {
+        if (c->D == 3) launch_step<double, 3>((const double*)low, (const double*)up, load_elem<double>(c->tm), load_elem<double>(rtol), load_elem<double>(atol), level, nranks, (const double*)partials_dev, (double*)state_dev, s);
+        else launch_step<double, 2>((const double*)low, (const double*)up, load_elem<double>(c->tm), load_elem<double>(rtol), load_elem<double>(atol), level, nranks, (const double*)partials_dev, (double*)state_dev, s);
+    } else if (c->dtype == FTS_F32) {
+        if (c->D == 3) launch_step<float, 3>((const float*)low, (const float*)up, load_elem<float>(c->tm), load_elem<float>(rtol), load_elem<float>(atol), level, nranks, (const float*)partials_dev, (float*)state_dev, s);
+        else launch_step<float, 2>((const float*)low, (const float*)up, load_elem<float>(c->tm), load_elem<float>(rtol), load_elem<float>(atol), level, nranks, (const float*)partials_dev, (float*)state_dev, s);
+    } else {
+        return set_error(FTS_ERR_UNSUPPORTED, "sharded step: f32/f64 only");
+    }
+    FTS_CUDA(cudaGetLastError());
+    return FTS_OK;
+}
+
+// ------------------------------------------------------------------------------- FMA peak ----
+// Register-resident chains: 8 independent accumulators per thread, 64 FMAs per loop trip.
+template <class T> __global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b)
+{
+    T r0 = a, r1 = a + T(1), r2 = a + T(2), r3 = a + T(3), r4 = a + T(4), r5 = a + T(5), r6 = a + T(6), r7 = a + T(7);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            r0 = fts::fm::fma(r0, b, a); r1 = fts::fm::fma(r1, b, a); r2 = fts::fm::fma(r2, b, a); r3 = fts::fm::fma(r3, b, a);
+            r4 = fts::fm::fma(r4, b, a); r5 = fts::fm::fma(r5, b, a); r6 = fts::fm::fma(r6, b, a); r7 = fts::fm::fma(r7, b, a);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+
+extern "C" int fts_measure_fma_peak(int dtype, int iters, double* tflops_out, double* ms_out)
+{
+    if (int rc = ensure_init()) return rc;
+    if (dtype != FTS_F32 && dtype != FTS_F64) return set_error(FTS_ERR_INVALID_ARGUMENT, "fma peak: f32 or f64");
+    if (iters <= 0) iters = 4096;
+    const int blocks = g_prop.multiProcessorCount * 8, threads = 256;
+    void* d = nullptr;
+    FTS_CUDA(cudaMalloc(&d, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    FTS_CUDA(cudaEventCreate(&e0));
+    FTS_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        FTS_CUDA(cudaEventRecord(e0, g_stream));
+        if (dtype == FTS_F64) k_fma_peak<double><<<blocks, threads, 0, g_stream>>>((double*)d, iters, 1.0000001, 0.9999999);
+        else k_fma_peak<float><<<blocks, threads, 0, g_stream>>>((float*)d, iters, 1.0001f, 0.9999f);
+        g_launches.fetch_add(1);
+        FTS_CUDA(cudaEventRecord(e1, g_stream));
+        FTS_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        FTS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    FTS_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return FTS_OK;
+}

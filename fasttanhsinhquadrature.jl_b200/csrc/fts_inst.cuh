@@ -1,0 +1,65 @@
+// fts_inst.cuh — explicit instantiation + registration of the kernel set of one builtin family.
+#pragma once
+#include "fts_families.cuh"
+#include "fts_internal.h"
+#include "fts_kernels.cuh"
+
+namespace fts_host {
+struct Registrar {
+    Registrar(const KernelEntry* e, int n) { register_kernels(e, n); }
+};
+}  // namespace fts_host
+
+#define FTS_KPTR(...) ((const void*)(&__VA_ARGS__))
+
+// f32 + f64, reference order and FAST, thread-per-integral kernels of a family
+#define FTS_REGISTER_TPI(FAM, FUNCTOR, FIXED_K, ADAPT_K)                                                     \
+    static const fts_host::KernelEntry k_entries_##FUNCTOR[] = {                                            \
+        {FAM, FTS_F32, fts_host::KID_FIXED_TPI, 0, FTS_KPTR(fts::FIXED_K<float, fts::FUNCTOR, false>)},     \
+        {FAM, FTS_F32, fts_host::KID_FIXED_TPI, 1, FTS_KPTR(fts::FIXED_K<float, fts::FUNCTOR, true>)},      \
+        {FAM, FTS_F64, fts_host::KID_FIXED_TPI, 0, FTS_KPTR(fts::FIXED_K<double, fts::FUNCTOR, false>)},    \
+        {FAM, FTS_F64, fts_host::KID_FIXED_TPI, 1, FTS_KPTR(fts::FIXED_K<double, fts::FUNCTOR, true>)},     \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::ADAPT_K<float, fts::FUNCTOR, false>)},     \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_TPI, 1, FTS_KPTR(fts::ADAPT_K<float, fts::FUNCTOR, true>)},      \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::ADAPT_K<double, fts::FUNCTOR, false>)},    \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_TPI, 1, FTS_KPTR(fts::ADAPT_K<double, fts::FUNCTOR, true>)},     \
+    };                                                                                                       \
+    static fts_host::Registrar k_reg_##FUNCTOR(k_entries_##FUNCTOR, 8);
+
+// adaptive-only families (complement kinds have no exported fixed-grid entry point)
+#define FTS_REGISTER_ADAPT_ONLY(FAM, FUNCTOR, ...)                                                           \
+    static const fts_host::KernelEntry k_entries_##FUNCTOR[] = {                                            \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::__VA_ARGS__<float, fts::FUNCTOR, false>)}, \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_TPI, 1, FTS_KPTR(fts::__VA_ARGS__<float, fts::FUNCTOR, true>)},  \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::__VA_ARGS__<double, fts::FUNCTOR, false>)},\
+        {FAM, FTS_F64, fts_host::KID_ADAPT_TPI, 1, FTS_KPTR(fts::__VA_ARGS__<double, fts::FUNCTOR, true>)}, \
+    };                                                                                                       \
+    static fts_host::Registrar k_reg_##FUNCTOR(k_entries_##FUNCTOR, 4);
+
+
+#include "fts_kernels_cta.cuh"
+
+// cooperative FAST kernels (CTA per integral) of a family, f32 + f64
+#define FTS_REGISTER_CTA(FAM, FUNCTOR, FIXED_K, ADAPT_K)                                                 \
+    static const fts_host::KernelEntry k_cta_entries_##FUNCTOR[] = {                                    \
+        {FAM, FTS_F32, fts_host::KID_FIXED_CTA, 1, FTS_KPTR(fts::FIXED_K<float, fts::FUNCTOR>)},        \
+        {FAM, FTS_F64, fts_host::KID_FIXED_CTA, 1, FTS_KPTR(fts::FIXED_K<double, fts::FUNCTOR>)},       \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_CTA, 1, FTS_KPTR(fts::ADAPT_K<float, fts::FUNCTOR>)},        \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_CTA, 1, FTS_KPTR(fts::ADAPT_K<double, fts::FUNCTOR>)},       \
+    };                                                                                                   \
+    static fts_host::Registrar k_cta_reg_##FUNCTOR(k_cta_entries_##FUNCTOR, 4);
+
+#define FTS_REGISTER_CTA_ADAPT_ONLY(FAM, FUNCTOR, ADAPT_K)                                               \
+    static const fts_host::KernelEntry k_cta_entries_##FUNCTOR[] = {                                    \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_CTA, 1, FTS_KPTR(fts::ADAPT_K<float, fts::FUNCTOR>)},        \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_CTA, 1, FTS_KPTR(fts::ADAPT_K<double, fts::FUNCTOR>)},       \
+    };                                                                                                   \
+    static fts_host::Registrar k_cta_reg_##FUNCTOR(k_cta_entries_##FUNCTOR, 2);
+
+// one-level whole-grid kernels (single large integral / multi-GPU shards), f32 + f64
+#define FTS_REGISTER_GRID(FAM, FUNCTOR, D)                                                               \
+    static const fts_host::KernelEntry k_grid_entries_##FUNCTOR[] = {                                   \
+        {FAM, FTS_F32, fts_host::KID_LEVEL_GRID, 1, FTS_KPTR(fts::k_level_grid<float, fts::FUNCTOR, D>)},  \
+        {FAM, FTS_F64, fts_host::KID_LEVEL_GRID, 1, FTS_KPTR(fts::k_level_grid<double, fts::FUNCTOR, D>)}, \
+    };                                                                                                   \
+    static fts_host::Registrar k_grid_reg_##FUNCTOR(k_grid_entries_##FUNCTOR, 2);

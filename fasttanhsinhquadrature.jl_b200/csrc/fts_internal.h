@@ -1,0 +1,70 @@
+// fts_internal.h — host-side internals shared by the translation units of libfts_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/fts_b200.h"
+
+namespace fts_host {
+
+// kernel ids of the registry (one entry per family x dtype x kernel x FAST)
+enum KernelId : int {
+    KID_FIXED_TPI = 0,     // k_fixed{1,2,3}d_tpi          thread per integral
+    KID_ADAPT_TPI = 1,     // k_adaptive{1d,1d_cmpl,2d,3d}_tpi
+    KID_FIXED_CTA = 2,     // k_fixed*_cta                 CTA per integral (FAST only)
+    KID_ADAPT_CTA = 3,     // k_adaptive*_cta              CTA per integral (FAST only)
+    KID_LEVEL_GRID = 4,    // k_level*_grid                many CTAs per integral, one launch per level
+    KID_COUNT = 5
+};
+
+struct KernelEntry {
+    int family, dtype, kid, fast;
+    const void* fn;  // __global__ host stub (static) or cudaKernel_t (NVRTC)
+};
+
+void register_kernels(const KernelEntry* entries, int count);
+const void* find_kernel(int family, int dtype, int kid, int fast);
+
+int set_error(int code, const std::string& msg);
+int cuda_error(cudaError_t e, const char* what);
+
+struct FamilyInfo {
+    int family, kind, nparams;
+    const char* name;
+};
+const FamilyInfo* family_info(int family);
+
+inline size_t dtype_size(int dtype) { return dtype == FTS_F32 ? 4 : (dtype == FTS_F64 ? 8 : 16); }
+
+}  // namespace fts_host
+
+struct fts_tables_s {
+    int dtype, n;
+    void* d_grid;         // Node<T>[n]
+    unsigned char h[16];  // one element
+};
+
+struct fts_cache_s {
+    int dtype, D, kind, max_levels;  // D = 0 for 1D caches; kind: 0 regular, 1 complement
+    long long count;                 // nodes in the flat level arrays
+    void* d_nodes;                   // Node<T>[count]
+    void* d_nodes_c;                 // NodeC<T>[count] (complement caches only)
+    unsigned char tm[16], ix[32], iw[32], ic[32];
+};
+
+struct fts_integrand_s {
+    int builtin, family, kind, nparams;
+    void* module;  // NVRTC integrands: compiled module (fts_nvrtc.cpp)
+};
+
+// fts_nvrtc.cpp: kernel of an NVRTC module (loads the cubin on first use); null + last_error on failure
+const void* fts_nvrtc_kernel(void* module, int dtype, int kid, int fast);
+
+#define FTS_CUDA(call)                                                     \
+    do {                                                                   \
+        cudaError_t e__ = (call);                                          \
+        if (e__ != cudaSuccess) return fts_host::cuda_error(e__, #call);   \
+    } while (0)

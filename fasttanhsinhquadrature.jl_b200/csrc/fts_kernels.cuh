@@ -1,0 +1,588 @@
+// fts_kernels.cuh — sm_100a kernels of the tanh-sinh hot path (fixed grids + adaptive levels).
+//
+// Two kernel styles per problem class:
+//   *_tpi  thread-per-integral, FTS_ORDER_REFERENCE: the literal sequential summation order and
+//          un-contracted arithmetic of the reference's scalar kernels (what quad/quad_cmpl/
+//          integrate*D compute).  Node tables are read with warp-uniform 128-bit loads
+//          (all lanes of a warp walk the same level), per-integral data is coalesced.
+//   *_cta  CTA-per-integral, FTS_ORDER_FAST: nodes of a level are dealt to the threads of the
+//          CTA, FMA accumulation, compensated (TwoSum) warp-shuffle + shared-memory merge,
+//          on-device stop test (the analogue of the reference's @turbo `_avx` twins).
+//
+// Every kernel takes ONE POD argument block (fts::Args<T>) so that statically compiled builtin
+// families and NVRTC-compiled user integrands are launched through the same code path.
+// This header is fed verbatim to NVRTC: no host includes.
+#pragma once
+#include "fts_math.cuh"
+
+namespace fts {
+
+enum : int { OPT_QUAD_EDGE = 1 };
+enum : int { FLAG_CONVERGED = 1, FLAG_MAX_LEVELS = 2, FLAG_ZERO_WIDTH = 4, FLAG_FLIPPED = 8 };
+
+template <class T> struct Node { T x, w; };             // 1D / tensor tables, interleaved
+template <class T> struct NodeC { T x, w, c, pad; };    // complement tables
+
+template <class T> struct Args {
+    // fixed grid (x,w,h) = tanhsinh(T,N)
+    const Node<T>* grid;
+    int n;
+    T h;
+    // adaptive level tables (flat, level offsets implied: 1D 2^l-2, tensor 2^(l+1)-4)
+    const Node<T>* nodes;
+    const NodeC<T>* nodes_c;
+    T tm;
+    T ix[2], iw[2], ic[2];
+    // per-integral inputs
+    const T* low;
+    const T* up;
+    int bstride;
+    const T* params;
+    int pstride;
+    T rtol, atol;
+    int max_levels;
+    int options;
+    long long batch;
+    // outputs
+    T* value;
+    T* err;
+    int* levels;
+    int* flags;
+    // grid-per-level kernels (one large integral, optionally sharded over ranks)
+    int level;            // level computed by this launch (0 = base grid)
+    int rank, nranks;     // shard of the flat new-cell index handled by this device
+    T* block_partials;    // [gridDim.x][2] compensated per-CTA partials (s, c)
+    unsigned int* ticket; // last-CTA election
+    T* partial_out;       // [2] this rank's (s, c) of the level
+    const T* state;       // [8] see fts_adaptive_sharded_step_dev; state[5] != 0 -> already converged
+};
+
+template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP > 0 ? NP : 1], const Args<T>& a, long long b)
+{
+#pragma unroll
+    for (int k = 0; k < NP; ++k) p[k] = a.params[b * a.pstride + k];
+    if (NP == 0) p[0] = num<T>::zero();
+}
+
+template <class T> __device__ __forceinline__ Node<T> ldg_node(const Node<T>* p) { return *p; }
+template <> __device__ __forceinline__ Node<double> ldg_node<double>(const Node<double>* p)
+{
+    double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    Node<double> r;
+    r.x = v.x;
+    r.w = v.y;
+    return r;
+}
+template <> __device__ __forceinline__ Node<float> ldg_node<float>(const Node<float>* p)
+{
+    float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    Node<float> r;
+    r.x = v.x;
+    r.w = v.y;
+    return r;
+}
+
+template <class T> __device__ __forceinline__ void store_result(const Args<T>& a, long long b, T value, T err, int level, int flags)
+{
+    a.value[b] = value;
+    if (a.err) a.err[b] = err;
+    if (a.levels) a.levels[b] = level;
+    if (a.flags) a.flags[b] = flags;
+}
+
+// quad()/quad_cmpl() edge rules for one axis (quad.jl:41-46,303-308): returns false when the
+// integral is identically zero; flips bounds and toggles `neg` when low > up.
+template <class T> __device__ __forceinline__ bool quad_edge_axis(T& lo, T& hi, bool& neg)
+{
+    if (lo == hi) return false;
+    if (lo > hi) {
+        T t = lo;
+        lo = hi;
+        hi = t;
+        neg = !neg;
+    }
+    return true;
+}
+
+// =================================================================== fixed grids, reference order
+// integrate1D(f, low, up, x, w, h)   /root/reference/src/integrate1D.jl:90-102
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_fixed1d_tpi(const Args<T> a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);  // core.jl:27-30
+    T s = num<T>::half_pi() * F::template eval<T, FAST>(x0, p);
+    const int n = a.n;
+    for (int i = 0; i < n; ++i) {
+        const Node<T> nd = ldg_node(a.grid + i);
+        const T d = dx * nd.x;
+        const T xp = x0 + d, xm = x0 - d;
+        s = muladd<T, FAST>(nd.w, F::template eval<T, FAST>(xm, p) + F::template eval<T, FAST>(xp, p), s);
+    }
+    a.value[b] = dx * a.h * s;
+}
+
+// integrate2D(f, low, up, x, w, h)   /root/reference/src/integrate2D.jl:91-124
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_fixed2d_tpi(const Args<T> a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T* lo = a.low + b * a.bstride;
+    const T* hi = a.up + b * a.bstride;
+    const T dx = half * (hi[0] - lo[0]), x0 = half * (hi[0] + lo[0]);
+    const T dy = half * (hi[1] - lo[1]), y0 = half * (hi[1] + lo[1]);
+    const T w0 = num<T>::half_pi();
+    const T w02 = w0 * w0;
+    T s = w02 * F::template eval<T, FAST>(x0, y0, p);
+    const int n = a.n;
+    for (int k = 0; k < n; ++k) {
+        const Node<T> nd = ldg_node(a.grid + k);
+        const T xkp = dx * nd.x + x0, xkm = x0 - dx * nd.x;
+        const T ykp = dy * nd.x + y0, ykm = y0 - dy * nd.x;
+        s = s + nd.w * w0 * (F::template eval<T, FAST>(xkp, y0, p) + F::template eval<T, FAST>(xkm, y0, p) +
+                             F::template eval<T, FAST>(x0, ykp, p) + F::template eval<T, FAST>(x0, ykm, p));
+    }
+    for (int i = 0; i < n; ++i) {
+        const Node<T> ni = ldg_node(a.grid + i);
+        const T xip = dx * ni.x + x0, xim = x0 - dx * ni.x;
+        T inner = num<T>::zero();
+        for (int j = 0; j < n; ++j) {
+            const Node<T> nj = ldg_node(a.grid + j);
+            const T yjp = dy * nj.x + y0, yjm = y0 - dy * nj.x;
+            inner = inner + nj.w * (F::template eval<T, FAST>(xim, yjm, p) + F::template eval<T, FAST>(xip, yjm, p) +
+                                    F::template eval<T, FAST>(xim, yjp, p) + F::template eval<T, FAST>(xip, yjp, p));
+        }
+        s = s + ni.w * inner;
+    }
+    a.value[b] = dx * dy * (a.h * a.h) * s;
+}
+
+// integrate3D(f, low, up, x, w, h)   /root/reference/src/integrate3D.jl:150-207
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_fixed3d_tpi(const Args<T> a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T* lo = a.low + b * a.bstride;
+    const T* hi = a.up + b * a.bstride;
+    const T dx = half * (hi[0] - lo[0]), x0 = half * (hi[0] + lo[0]);
+    const T dy = half * (hi[1] - lo[1]), y0 = half * (hi[1] + lo[1]);
+    const T dz = half * (hi[2] - lo[2]), z0 = half * (hi[2] + lo[2]);
+    const T w0 = num<T>::half_pi();
+    const T w02 = w0 * w0;
+    const T w03 = w02 * w0;
+#define FE(X, Y, Z) F::template eval<T, FAST>(X, Y, Z, p)
+    T total = w03 * FE(x0, y0, z0);
+    const int n = a.n;
+    for (int i = 0; i < n; ++i) {
+        const Node<T> nd = ldg_node(a.grid + i);
+        const T axis = (FE(dx * nd.x + x0, y0, z0) + FE(x0 - dx * nd.x, y0, z0)) + (FE(x0, dy * nd.x + y0, z0) + FE(x0, y0 - dy * nd.x, z0)) +
+                       (FE(x0, y0, dz * nd.x + z0) + FE(x0, y0, z0 - dz * nd.x));
+        total = total + nd.w * w02 * axis;
+    }
+    for (int i = 0; i < n; ++i) {
+        const Node<T> ni = ldg_node(a.grid + i);
+        const T xp = dx * ni.x + x0, xm = x0 - dx * ni.x;
+        const T ypi = dy * ni.x + y0, ymi = y0 - dy * ni.x;
+        for (int j = 0; j < n; ++j) {
+            const Node<T> nj = ldg_node(a.grid + j);
+            const T wiwj = ni.w * nj.w;
+            const T yp = dy * nj.x + y0, ym = y0 - dy * nj.x;
+            const T zpj = dz * nj.x + z0, zmj = z0 - dz * nj.x;
+            const T plane = (FE(xp, yp, z0) + FE(xm, yp, z0) + FE(xp, ym, z0) + FE(xm, ym, z0)) +
+                            (FE(xp, y0, zpj) + FE(xm, y0, zpj) + FE(xp, y0, zmj) + FE(xm, y0, zmj)) +
+                            (FE(x0, ypi, zpj) + FE(x0, ymi, zpj) + FE(x0, ypi, zmj) + FE(x0, ymi, zmj));
+            total = total + wiwj * w0 * plane;
+            T oct = num<T>::zero();
+            for (int k = 0; k < n; ++k) {
+                const Node<T> nk = ldg_node(a.grid + k);
+                const T zp = dz * nk.x + z0, zm = z0 - dz * nk.x;
+                oct = oct + nk.w * ((FE(xp, yp, zp) + FE(xm, yp, zp) + FE(xp, ym, zp) + FE(xm, ym, zp)) +
+                                    (FE(xp, yp, zm) + FE(xm, yp, zm) + FE(xp, ym, zm) + FE(xm, ym, zm)));
+            }
+            total = total + wiwj * oct;
+        }
+    }
+#undef FE
+    a.value[b] = (dx * dy * dz * (a.h * a.h * a.h)) * total;
+}
+
+// =================================================================== adaptive, reference order
+// adaptive_integrate_1D typed core   /root/reference/src/adaptive.jl:28-75
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_adaptive1d_tpi(const Args<T> a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    bool neg = false;
+    int flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        if (!quad_edge_axis(lo, hi, neg)) {
+            store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+            return;
+        }
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    T h = a.tm * half;
+    const T w0 = num<T>::pi() * half;
+    T s_total = w0 * F::template eval<T, FAST>(x0, p);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T xk = a.ix[i];
+        s_total = s_total + a.iw[i] * (F::template eval<T, FAST>(dx * xk + x0, p) + F::template eval<T, FAST>(x0 - dx * xk, p));
+    }
+    T old_res = dx * h * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    const Node<T>* __restrict__ nodes = a.nodes;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        T s_new = num<T>::zero();
+        const int n = 1 << level;
+        const Node<T>* __restrict__ lv = nodes + (n - 2);
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) {
+            const Node<T> nd = ldg_node(lv + i);
+            const T d = dx * nd.x;
+            const T xp = d + x0, xm = x0 - d;
+            s_new = muladd<T, FAST>(nd.w, F::template eval<T, FAST>(xp, p) + F::template eval<T, FAST>(xm, p), s_new);
+        }
+        s_total = s_total + s_new;
+        const T new_res = dx * h * s_total;
+        err = fm::abs(new_res - old_res);
+        level_used = level;
+        old_res = new_res;
+        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+            flags |= FLAG_CONVERGED;
+            break;
+        }
+    }
+    if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+    store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+}
+
+// adaptive_integrate_1D_cmpl typed core   /root/reference/src/adaptive.jl:727-785
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_adaptive1d_cmpl_tpi(const Args<T> a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half(), one = num<T>::one();
+    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    bool neg = false;
+    int flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        if (!quad_edge_axis(lo, hi, neg)) {
+            store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+            return;
+        }
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    T h = a.tm * half;
+    const T w0 = num<T>::half_pi();
+    T s_total = w0 * F::template eval<T, FAST>(x0, dx, dx, p);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T xk = a.ix[i], ck = a.ic[i], wk = a.iw[i];
+        const T dxck = dx * ck;
+        const T dx1pxk = dx * (one + xk);
+        s_total = s_total + wk * (F::template eval<T, FAST>(dx * xk + x0, dxck, dx1pxk, p) + F::template eval<T, FAST>(x0 - dx * xk, dx1pxk, dxck, p));
+    }
+    T old_res = dx * h * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        T s_new = num<T>::zero();
+        const int n = 1 << level;
+        const NodeC<T>* __restrict__ lv = a.nodes_c + (n - 2);
+        for (int i = 0; i < n; ++i) {
+            const NodeC<T> nd = lv[i];
+            const T dxck = dx * nd.c;
+            const T dx1pxk = dx * (one + nd.x);
+            const T d = dx * nd.x;
+            s_new = muladd<T, FAST>(nd.w, F::template eval<T, FAST>(d + x0, dxck, dx1pxk, p) + F::template eval<T, FAST>(x0 - d, dx1pxk, dxck, p), s_new);
+        }
+        s_total = s_total + s_new;
+        const T new_res = dx * h * s_total;
+        err = fm::abs(new_res - old_res);
+        level_used = level;
+        old_res = new_res;
+        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+            flags |= FLAG_CONVERGED;
+            break;
+        }
+    }
+    if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+    store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+}
+
+// integrand functors of kind FTS_KIND_2D_CMPL specialise this to true
+template <class F> struct is_cmpl2d { static constexpr bool value = false; };
+
+// ---- 2D helpers (adaptive.jl:165-176)
+template <class T> struct Box2 { T dx, x0, dy, y0, w0; };
+
+template <class T, class F, bool FAST> __device__ __forceinline__ T quadrants(const Box2<T>& bx, const T* p, T xi, T yi, T wi, T wj)
+{
+    const T xp = bx.dx * xi + bx.x0, xm = bx.x0 - bx.dx * xi;
+    const T yp = bx.dy * yi + bx.y0, ym = bx.y0 - bx.dy * yi;
+    return wi * wj * (F::template eval<T, FAST>(xp, yp, p) + F::template eval<T, FAST>(xm, yp, p) + F::template eval<T, FAST>(xp, ym, p) + F::template eval<T, FAST>(xm, ym, p));
+}
+template <class T, class F, bool FAST> __device__ __forceinline__ T axes2(const Box2<T>& bx, const T* p, T v, T wk)
+{
+    const T xp = bx.dx * v + bx.x0, xm = bx.x0 - bx.dx * v;
+    const T yp = bx.dy * v + bx.y0, ym = bx.y0 - bx.dy * v;
+    return wk * bx.w0 * (F::template eval<T, FAST>(xp, bx.y0, p) + F::template eval<T, FAST>(xm, bx.y0, p) + F::template eval<T, FAST>(bx.x0, yp, p) + F::template eval<T, FAST>(bx.x0, ym, p));
+}
+// tensor-complement twins (extension for BASELINE config C; coordinates as adaptive.jl:764-769 per axis)
+template <class T, class F, bool FAST> __device__ __forceinline__ T quadrants_c(const Box2<T>& bx, const T* p, T xi, T ci, T yj, T cj, T wi, T wj)
+{
+    const T one = num<T>::one();
+    const T xp = bx.dx * xi + bx.x0, xm = bx.x0 - bx.dx * xi;
+    const T yp = bx.dy * yj + bx.y0, ym = bx.y0 - bx.dy * yj;
+    const T bxp = bx.dx * ci, axp = bx.dx * (one + xi);
+    const T dyp = bx.dy * cj, cyp = bx.dy * (one + yj);
+    return wi * wj * (F::template eval<T, FAST>(xp, yp, bxp, axp, dyp, cyp, p) + F::template eval<T, FAST>(xm, yp, axp, bxp, dyp, cyp, p) +
+                      F::template eval<T, FAST>(xp, ym, bxp, axp, cyp, dyp, p) + F::template eval<T, FAST>(xm, ym, axp, bxp, cyp, dyp, p));
+}
+template <class T, class F, bool FAST> __device__ __forceinline__ T axes2_c(const Box2<T>& bx, const T* p, T v, T c, T wk)
+{
+    const T one = num<T>::one();
+    const T xp = bx.dx * v + bx.x0, xm = bx.x0 - bx.dx * v;
+    const T yp = bx.dy * v + bx.y0, ym = bx.y0 - bx.dy * v;
+    const T bxc = bx.dx * c, ax = bx.dx * (one + v);
+    const T dyc = bx.dy * c, cy = bx.dy * (one + v);
+    return wk * bx.w0 * (F::template eval<T, FAST>(xp, bx.y0, bxc, ax, bx.dy, bx.dy, p) + F::template eval<T, FAST>(xm, bx.y0, ax, bxc, bx.dy, bx.dy, p) +
+                         F::template eval<T, FAST>(bx.x0, yp, bx.dx, bx.dx, dyc, cy, p) + F::template eval<T, FAST>(bx.x0, ym, bx.dx, bx.dx, cy, dyc, p));
+}
+
+// common prologue for 2D/3D boxes: loads bounds, applies quad edge rules (quad.jl:96-115,129-153)
+template <int D, class T> __device__ __forceinline__ bool load_box(const Args<T>& a, long long b, T (&lo)[D], T (&hi)[D], bool& neg, int& flags)
+{
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        lo[d] = a.low[b * a.bstride + d];
+        hi[d] = a.up[b * a.bstride + d];
+    }
+    neg = false;
+    flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        bool zero = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) zero = zero || (lo[d] == hi[d]);
+        if (zero) return false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) quad_edge_axis(lo[d], hi[d], neg);
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    return true;
+}
+
+// adaptive_integrate_2D typed core   /root/reference/src/adaptive.jl:154-224
+// CMPL=true: tensor-complement extension on NodeC tables (BASELINE config C)
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_adaptive2d_tpi(const Args<T> a)
+{
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[2], hi[2];
+    bool neg;
+    int flags;
+    if (!load_box<2>(a, b, lo, hi, neg, flags)) {
+        store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        return;
+    }
+    const T half = num<T>::half();
+    Box2<T> bx;
+    bx.dx = half * (hi[0] - lo[0]); bx.x0 = half * (hi[0] + lo[0]);
+    bx.dy = half * (hi[1] - lo[1]); bx.y0 = half * (hi[1] + lo[1]);
+    bx.w0 = num<T>::half_pi();
+    T h = a.tm * half;
+    const T w02 = bx.w0 * bx.w0;
+    T s_total;
+    if constexpr (CMPL) s_total = w02 * F::template eval<T, FAST>(bx.x0, bx.y0, bx.dx, bx.dx, bx.dy, bx.dy, p);
+    else s_total = w02 * F::template eval<T, FAST>(bx.x0, bx.y0, p);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if constexpr (CMPL) s_total = s_total + quadrants_c<T, F, FAST>(bx, p, a.ix[i], a.ic[i], a.ix[j], a.ic[j], a.iw[i], a.iw[j]);
+            else s_total = s_total + quadrants<T, F, FAST>(bx, p, a.ix[i], a.ix[j], a.iw[i], a.iw[j]);
+        }
+        if constexpr (CMPL) s_total = s_total + axes2_c<T, F, FAST>(bx, p, a.ix[i], a.ic[i], a.iw[i]);
+        else s_total = s_total + axes2<T, F, FAST>(bx, p, a.ix[i], a.iw[i]);
+    }
+    T old_res = bx.dx * bx.dy * (h * h) * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        T s_new = num<T>::zero();
+        const int n = 2 << level;
+        const int off = n - 4;
+        for (int i = 1; i <= n; ++i) {
+            T xi, wi, ci = num<T>::zero();
+            if constexpr (CMPL) { const NodeC<T> nd = a.nodes_c[off + i - 1]; xi = nd.x; wi = nd.w; ci = nd.c; }
+            else { const Node<T> nd = ldg_node(a.nodes + off + i - 1); xi = nd.x; wi = nd.w; }
+            const int jstep = (i & 1) ? 1 : 2;  // even i: only odd j are new (adaptive.jl:203)
+            for (int j = 1; j <= n; j += jstep) {
+                if constexpr (CMPL) { const NodeC<T> nj = a.nodes_c[off + j - 1]; s_new = s_new + quadrants_c<T, F, FAST>(bx, p, xi, ci, nj.x, nj.c, wi, nj.w); }
+                else { const Node<T> nj = ldg_node(a.nodes + off + j - 1); s_new = s_new + quadrants<T, F, FAST>(bx, p, xi, nj.x, wi, nj.w); }
+            }
+            if (i & 1) {
+                if constexpr (CMPL) s_new = s_new + axes2_c<T, F, FAST>(bx, p, xi, ci, wi);
+                else s_new = s_new + axes2<T, F, FAST>(bx, p, xi, wi);
+            }
+        }
+        s_total = s_total + s_new;
+        const T new_res = bx.dx * bx.dy * (h * h) * s_total;
+        err = fm::abs(new_res - old_res);
+        level_used = level;
+        old_res = new_res;
+        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+            flags |= FLAG_CONVERGED;
+            break;
+        }
+    }
+    if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+    store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+}
+
+// ---- 3D helpers (adaptive.jl:365-403)
+template <class T> struct Box3 { T dx, x0, dy, y0, dz, z0, w0, w02; };
+
+template <class T, class F, bool FAST> __device__ __forceinline__ T octant(const Box3<T>& bx, const T* p, T vi, T vj, T vk, T wi, T wj, T wk)
+{
+    const T xp = bx.dx * vi + bx.x0, xm = bx.x0 - bx.dx * vi;
+    const T yp = bx.dy * vj + bx.y0, ym = bx.y0 - bx.dy * vj;
+    const T zp = bx.dz * vk + bx.z0, zm = bx.z0 - bx.dz * vk;
+    const T w = wi * wj * wk;
+#define FE(X, Y, Z) F::template eval<T, FAST>(X, Y, Z, p)
+    return w * ((FE(xp, yp, zp) + FE(xm, yp, zp) + FE(xp, ym, zp) + FE(xm, ym, zp)) + (FE(xp, yp, zm) + FE(xm, yp, zm) + FE(xp, ym, zm) + FE(xm, ym, zm)));
+}
+template <class T, class F, bool FAST> __device__ __forceinline__ T planes(const Box3<T>& bx, const T* p, T vi, T vj, T wi, T wj)
+{
+    const T x0 = bx.x0, y0 = bx.y0, z0 = bx.z0;
+    const T xp = bx.dx * vi + x0, xm = x0 - bx.dx * vi;
+    const T ypi = bx.dy * vi + y0, ymi = y0 - bx.dy * vi;
+    const T ypj = bx.dy * vj + y0, ymj = y0 - bx.dy * vj;
+    const T zpj = bx.dz * vj + z0, zmj = z0 - bx.dz * vj;
+    const T w = wi * wj * bx.w0;
+    return w * ((FE(xp, ypj, z0) + FE(xm, ypj, z0) + FE(xp, ymj, z0) + FE(xm, ymj, z0)) + (FE(xp, y0, zpj) + FE(xm, y0, zpj) + FE(xp, y0, zmj) + FE(xm, y0, zmj)) +
+                (FE(x0, ypi, zpj) + FE(x0, ymi, zpj) + FE(x0, ypi, zmj) + FE(x0, ymi, zmj)));
+}
+template <class T, class F, bool FAST> __device__ __forceinline__ T axes3(const Box3<T>& bx, const T* p, T vi, T wi)
+{
+    const T x0 = bx.x0, y0 = bx.y0, z0 = bx.z0;
+    const T xp = bx.dx * vi + x0, xm = x0 - bx.dx * vi;
+    const T yp = bx.dy * vi + y0, ym = y0 - bx.dy * vi;
+    const T zp = bx.dz * vi + z0, zm = z0 - bx.dz * vi;
+    const T w = wi * bx.w02;
+    return w * ((FE(xp, y0, z0) + FE(xm, y0, z0)) + (FE(x0, yp, z0) + FE(x0, ym, z0)) + (FE(x0, y0, zp) + FE(x0, y0, zm)));
+}
+#undef FE
+
+template <class T> __device__ __forceinline__ Box3<T> make_box3(const T* lo, const T* hi)
+{
+    const T half = num<T>::half();
+    Box3<T> bx;
+    bx.dx = half * (hi[0] - lo[0]); bx.x0 = half * (hi[0] + lo[0]);
+    bx.dy = half * (hi[1] - lo[1]); bx.y0 = half * (hi[1] + lo[1]);
+    bx.dz = half * (hi[2] - lo[2]); bx.z0 = half * (hi[2] + lo[2]);
+    bx.w0 = num<T>::half_pi();
+    bx.w02 = bx.w0 * bx.w0;
+    return bx;
+}
+
+// level-0 sum (adaptive.jl:406-418)
+template <class T, class F, bool FAST> __device__ __forceinline__ T level0_3d(const Box3<T>& bx, const T* p, const T (&ix)[2], const T (&iw)[2])
+{
+    const T w03 = bx.w02 * bx.w0;
+    T s_total = w03 * F::template eval<T, FAST>(bx.x0, bx.y0, bx.z0, p);
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) s_total = s_total + octant<T, F, FAST>(bx, p, ix[i], ix[j], ix[k], iw[i], iw[j], iw[k]);
+            s_total = s_total + planes<T, F, FAST>(bx, p, ix[i], ix[j], iw[i], iw[j]);
+        }
+        s_total = s_total + axes3<T, F, FAST>(bx, p, ix[i], iw[i]);
+    }
+    return s_total;
+}
+
+// adaptive_integrate_3D typed core   /root/reference/src/adaptive.jl:352-471
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_adaptive3d_tpi(const Args<T> a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[3], hi[3];
+    bool neg;
+    int flags;
+    if (!load_box<3>(a, b, lo, hi, neg, flags)) {
+        store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        return;
+    }
+    const T half = num<T>::half();
+    const Box3<T> bx = make_box3(lo, hi);
+    T h = a.tm * half;
+    T s_total = level0_3d<T, F, FAST>(bx, p, a.ix, a.iw);
+    T old_res = bx.dx * bx.dy * bx.dz * (h * h * h) * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        T s_new = num<T>::zero();
+        const int n = 2 << level;
+        const Node<T>* __restrict__ lv = a.nodes + (n - 4);
+        for (int i = 1; i <= n; ++i) {
+            const Node<T> ni = ldg_node(lv + i - 1);
+            for (int j = 1; j <= n; ++j) {
+                const Node<T> nj = ldg_node(lv + j - 1);
+                const bool full = (i & 1) || (j & 1);  // adaptive.jl:432-453 index classes
+                const int kstep = full ? 1 : 2;
+#pragma unroll 1
+                for (int k = 1; k <= n; k += kstep) {
+                    const Node<T> nk = ldg_node(lv + k - 1);
+                    s_new = s_new + octant<T, F, FAST>(bx, p, ni.x, nj.x, nk.x, ni.w, nj.w, nk.w);
+                }
+                if (full) s_new = s_new + planes<T, F, FAST>(bx, p, ni.x, nj.x, ni.w, nj.w);
+            }
+            if (i & 1) s_new = s_new + axes3<T, F, FAST>(bx, p, ni.x, ni.w);
+        }
+        s_total = s_total + s_new;
+        const T new_res = bx.dx * bx.dy * bx.dz * (h * h * h) * s_total;
+        err = fm::abs(new_res - old_res);
+        level_used = level;
+        old_res = new_res;
+        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+            flags |= FLAG_CONVERGED;
+            break;
+        }
+    }
+    if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+    store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+}
+
+}  // namespace fts

@@ -1,0 +1,700 @@
+// fts_kernels_cta.cuh — cooperative (FTS_ORDER_FAST) kernels: the analogue of the reference's
+// @turbo `_avx` twins (reassociated sums, FMA contraction), re-designed for the B200:
+//
+//   k_*_cta    one CTA per integral.  The coordinates x0±Δx·x_i (and y, z, weights, complement
+//              distances) of the current level are staged in SHARED memory by the whole CTA —
+//              the reference hoists them into per-cache scratch vectors that live in the globally
+//              memoised cache (adaptive.jl:570-580, a latent race); here the scratch is per CTA.
+//              The level's NEW cells (index-parity classes of adaptive.jl:199-209, 430-456) are
+//              enumerated by a flat index and dealt to threads with stride blockDim, so every
+//              thread gets the same number of cells (±1) whatever the class mix.
+//   k_level*_grid  one launch per refinement level, many CTAs per integral, for ONE large 2D/3D
+//              integral; the flat cell index is additionally dealt over `nranks` devices.  CTA
+//              partials are merged by the last CTA (ticket) in a fixed order -> deterministic.
+//
+// Sums: plain FMA inside a thread's short run, TwoSum-compensated (s, c) pairs for every merge
+// (warp shuffle -> shared memory -> CTA -> grid -> ranks) and for the running total across levels.
+#pragma once
+#include "fts_kernels.cuh"
+
+namespace fts {
+
+constexpr int CTA_THREADS = 256;
+
+template <class T> __device__ __forceinline__ Comp<T> warp_reduce(Comp<T> v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Comp<T> o;
+        o.s = __shfl_down_sync(0xffffffffu, v.s, off);
+        o.c = __shfl_down_sync(0xffffffffu, v.c, off);
+        v.merge(o);
+    }
+    return v;
+}
+
+// result valid in thread 0; `red` is shared memory for 64 elements; contains two barriers
+template <class T> __device__ __forceinline__ Comp<T> block_reduce(Comp<T> v, T* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_reduce(v);
+    if (lane == 0) {
+        red[2 * warp] = v.s;
+        red[2 * warp + 1] = v.c;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Comp<T> w;
+        if (lane < nw) {
+            w.s = red[2 * lane];
+            w.c = red[2 * lane + 1];
+        }
+        v = warp_reduce(w);
+    }
+    __syncthreads();
+    return v;
+}
+
+template <class T> __device__ __forceinline__ Comp<T> comp_of(T v)
+{
+    Comp<T> c;
+    c.s = v;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------ 1D -----
+// adaptive_integrate_1D_avx / adaptive_integrate_1D_cmpl_avx   adaptive.jl:94-133, 805-855
+template <class T, class F, bool CMPL> __device__ __forceinline__ void adaptive1d_cta_body(const Args<T>& a)
+{
+    __shared__ T red[64];
+    __shared__ int s_done;
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half(), one = num<T>::one();
+    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    bool neg = false;
+    int flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        if (!quad_edge_axis(lo, hi, neg)) {
+            if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+            return;
+        }
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    T h = a.tm * half;
+    // level 0: centre + 2 node pairs on threads 0..2
+    T acc = num<T>::zero();
+    if (tid == 0) {
+        if constexpr (CMPL) acc = num<T>::half_pi() * F::template eval<T, true>(x0, dx, dx, p);
+        else acc = num<T>::half_pi() * F::template eval<T, true>(x0, p);
+    } else if (tid <= 2) {
+        const T xk = a.ix[tid - 1], wk = a.iw[tid - 1];
+        const T d = dx * xk;
+        if constexpr (CMPL) {
+            const T dxck = dx * a.ic[tid - 1], dx1p = dx * (one + xk);
+            acc = wk * (F::template eval<T, true>(d + x0, dxck, dx1p, p) + F::template eval<T, true>(x0 - d, dx1p, dxck, p));
+        } else {
+            acc = wk * (F::template eval<T, true>(d + x0, p) + F::template eval<T, true>(x0 - d, p));
+        }
+    }
+    Comp<T> s_total = block_reduce(comp_of(acc), red);
+    T old_res = dx * h * s_total.value();
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 1 << level;
+        acc = num<T>::zero();
+        if constexpr (CMPL) {
+            const NodeC<T>* __restrict__ lv = a.nodes_c + (n - 2);
+            for (int i = tid; i < n; i += blockDim.x) {
+                const NodeC<T> nd = lv[i];
+                const T d = dx * nd.x, dxck = dx * nd.c, dx1p = dx * (one + nd.x);
+                acc = fm::fma(nd.w, F::template eval<T, true>(d + x0, dxck, dx1p, p) + F::template eval<T, true>(x0 - d, dx1p, dxck, p), acc);
+            }
+        } else {
+            const Node<T>* __restrict__ lv = a.nodes + (n - 2);
+            for (int i = tid; i < n; i += blockDim.x) {
+                const Node<T> nd = ldg_node(lv + i);
+                const T xp = fm::fma(dx, nd.x, x0), xm = fm::fma(-dx, nd.x, x0);
+                acc = fm::fma(nd.w, F::template eval<T, true>(xp, p) + F::template eval<T, true>(xm, p), acc);
+            }
+        }
+        const Comp<T> lv_sum = block_reduce(comp_of(acc), red);
+        if (tid == 0) {
+            s_total.merge(lv_sum);
+            const T new_res = dx * h * s_total.value();
+            err = fm::abs(new_res - old_res);
+            old_res = new_res;
+            level_used = level;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            if (conv) flags |= FLAG_CONVERGED;
+            s_done = conv ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive1d_cta(const Args<T> a) { adaptive1d_cta_body<T, F, false>(a); }
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive1d_cmpl_cta(const Args<T> a) { adaptive1d_cta_body<T, F, true>(a); }
+
+// integrate1D_avx   integrate1D.jl:138-147
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed1d_cta(const Args<T> a)
+{
+    __shared__ T red[64];
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    T acc = tid == 0 ? num<T>::half_pi() * F::template eval<T, true>(x0, p) : num<T>::zero();
+    for (int i = tid; i < a.n; i += blockDim.x) {
+        const Node<T> nd = ldg_node(a.grid + i);
+        const T xp = fm::fma(dx, nd.x, x0), xm = fm::fma(-dx, nd.x, x0);
+        acc = fm::fma(nd.w, F::template eval<T, true>(xm, p) + F::template eval<T, true>(xp, p), acc);
+    }
+    const Comp<T> s = block_reduce(comp_of(acc), red);
+    if (tid == 0) a.value[b] = dx * a.h * s.value();
+}
+
+// ------------------------------------------------------------------------------------ 2D -----
+template <class T> struct Sm2 {
+    T *xp, *xm, *yp, *ym, *w;   // hoisted coordinates and weights of the level
+    T *bx, *ax, *dyc, *cy;      // complement distances Δx·c, Δx·(1+x), Δy·c, Δy·(1+x)
+    T dx, x0, dy, y0, w0;
+};
+
+template <class T, bool CMPL> __device__ __forceinline__ size_t sm2_elems(int n) { return (size_t)(CMPL ? 9 : 5) * n; }
+
+template <class T, bool CMPL> __device__ __forceinline__ void sm2_carve(Sm2<T>& s, T* base, int n)
+{
+    s.xp = base; s.xm = base + n; s.yp = base + 2 * n; s.ym = base + 3 * n; s.w = base + 4 * n;
+    if (CMPL) { s.bx = base + 5 * n; s.ax = base + 6 * n; s.dyc = base + 7 * n; s.cy = base + 8 * n; }
+}
+
+// stage one level; `x,w,c` given as strided element pointers so that Node / NodeC / initial
+// tuples all fit (stride in elements)
+template <class T, bool CMPL>
+__device__ __forceinline__ void sm2_stage(Sm2<T>& s, const T* x, const T* w, const T* c, int stride, int n)
+{
+    const T one = num<T>::one();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const T xi = x[(size_t)i * stride], wi = w[(size_t)i * stride];
+        s.xp[i] = fm::fma(s.dx, xi, s.x0);
+        s.xm[i] = fm::fma(-s.dx, xi, s.x0);
+        s.yp[i] = fm::fma(s.dy, xi, s.y0);
+        s.ym[i] = fm::fma(-s.dy, xi, s.y0);
+        s.w[i] = wi;
+        if (CMPL) {
+            const T ci = c[(size_t)i * stride];
+            s.bx[i] = s.dx * ci;
+            s.ax[i] = s.dx * (one + xi);
+            s.dyc[i] = s.dy * ci;
+            s.cy[i] = s.dy * (one + xi);
+        }
+    }
+}
+
+template <class T, class F, bool CMPL> __device__ __forceinline__ T cell2(const Sm2<T>& s, const T* p, int i, int j)
+{
+    const T xp = s.xp[i], xm = s.xm[i], yp = s.yp[j], ym = s.ym[j];
+    T f;
+    if constexpr (CMPL) {
+        const T bx = s.bx[i], ax = s.ax[i], dyc = s.dyc[j], cy = s.cy[j];
+        f = (F::template eval<T, true>(xp, yp, bx, ax, dyc, cy, p) + F::template eval<T, true>(xm, yp, ax, bx, dyc, cy, p)) +
+            (F::template eval<T, true>(xp, ym, bx, ax, cy, dyc, p) + F::template eval<T, true>(xm, ym, ax, bx, cy, dyc, p));
+    } else {
+        f = (F::template eval<T, true>(xp, yp, p) + F::template eval<T, true>(xm, yp, p)) +
+            (F::template eval<T, true>(xp, ym, p) + F::template eval<T, true>(xm, ym, p));
+    }
+    return (s.w[i] * s.w[j]) * f;
+}
+
+template <class T, class F, bool CMPL> __device__ __forceinline__ T axis2(const Sm2<T>& s, const T* p, int i)
+{
+    T f;
+    if constexpr (CMPL) {
+        f = (F::template eval<T, true>(s.xp[i], s.y0, s.bx[i], s.ax[i], s.dy, s.dy, p) + F::template eval<T, true>(s.xm[i], s.y0, s.ax[i], s.bx[i], s.dy, s.dy, p)) +
+            (F::template eval<T, true>(s.x0, s.yp[i], s.dx, s.dx, s.dyc[i], s.cy[i], p) + F::template eval<T, true>(s.x0, s.ym[i], s.dx, s.dx, s.cy[i], s.dyc[i], p));
+    } else {
+        f = (F::template eval<T, true>(s.xp[i], s.y0, p) + F::template eval<T, true>(s.xm[i], s.y0, p)) +
+            (F::template eval<T, true>(s.x0, s.yp[i], p) + F::template eval<T, true>(s.x0, s.ym[i], p));
+    }
+    return (s.w[i] * s.w0) * f;
+}
+
+// Sum of the cells a thread owns.  all_new: every (i,j) (level 0 / fixed grids, n arbitrary);
+// otherwise n = 2^log2n and only cells with an odd 1-based index in i or j are new
+// (adaptive.jl:199-209): 0-based i even -> all j; i odd -> j even.
+template <class T, class F, bool CMPL>
+__device__ __forceinline__ T level_sum_2d(const Sm2<T>& s, const T* p, int n, int log2n, bool all_new, long long start, long long stride)
+{
+    T acc = num<T>::zero();
+    if (all_new) {
+        const long long ncell = (long long)n * n;
+        for (long long t = start; t < ncell; t += stride) {
+            const int i = (int)(t / n), j = (int)(t - (long long)i * n);
+            acc = acc + cell2<T, F, CMPL>(s, p, i, j);
+        }
+        for (long long t = start; t < n; t += stride) acc = acc + axis2<T, F, CMPL>(s, p, (int)t);
+    } else {
+        const long long nA = ((long long)n * n) >> 1, ncell = nA + (nA >> 1);
+        for (long long t = start; t < ncell; t += stride) {
+            int i, j;
+            if (t < nA) {
+                i = (int)(t >> log2n) << 1;
+                j = (int)(t & (n - 1));
+            } else {
+                const long long u = t - nA;
+                i = ((int)(u >> (log2n - 1)) << 1) | 1;
+                j = (int)(u & ((n >> 1) - 1)) << 1;
+            }
+            acc = acc + cell2<T, F, CMPL>(s, p, i, j);
+        }
+        for (long long t = start; t < (n >> 1); t += stride) acc = acc + axis2<T, F, CMPL>(s, p, (int)t << 1);
+    }
+    return acc;
+}
+
+extern __shared__ __align__(16) unsigned char fts_dyn_smem[];
+
+// adaptive_integrate_2D_avx (+ tensor-complement extension)   adaptive.jl:242-333
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive2d_cta(const Args<T> a)
+{
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    __shared__ T red[64];
+    __shared__ int s_done;
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[2], hi[2];
+    bool neg;
+    int flags;
+    if (!load_box<2>(a, b, lo, hi, neg, flags)) {
+        if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        return;
+    }
+    const T half = num<T>::half();
+    Sm2<T> s;
+    s.dx = half * (hi[0] - lo[0]); s.x0 = half * (hi[0] + lo[0]);
+    s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
+    s.w0 = num<T>::half_pi();
+    const int nmax = a.max_levels > 0 ? (2 << a.max_levels) : 2;
+    sm2_carve<T, CMPL>(s, reinterpret_cast<T*>(fts_dyn_smem), nmax);
+    T h = a.tm * half;
+    // level 0: base grid {h, 2h}, all cells new (adaptive.jl:264-272)
+    sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2);
+    __syncthreads();
+    T acc = level_sum_2d<T, F, CMPL>(s, p, 2, 1, true, tid, blockDim.x);
+    if (tid == 0) {
+        if constexpr (CMPL) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.dx, s.dx, s.dy, s.dy, p);
+        else acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
+    }
+    Comp<T> s_total = block_reduce(comp_of(acc), red);
+    T old_res = s.dx * s.dy * (h * h) * s_total.value();
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 2 << level;
+        if constexpr (CMPL) {
+            const NodeC<T>* lv = a.nodes_c + (n - 4);
+            sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n);
+        } else {
+            const Node<T>* lv = a.nodes + (n - 4);
+            sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n);
+        }
+        __syncthreads();
+        acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, false, tid, blockDim.x);
+        const Comp<T> lv_sum = block_reduce(comp_of(acc), red);
+        if (tid == 0) {
+            s_total.merge(lv_sum);
+            const T new_res = s.dx * s.dy * (h * h) * s_total.value();
+            err = fm::abs(new_res - old_res);
+            old_res = new_res;
+            level_used = level;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            if (conv) flags |= FLAG_CONVERGED;
+            s_done = conv ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
+// integrate2D_avx   integrate2D.jl:46-73
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed2d_cta(const Args<T> a)
+{
+    __shared__ T red[64];
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T* lo = a.low + b * a.bstride;
+    const T* hi = a.up + b * a.bstride;
+    Sm2<T> s;
+    s.dx = half * (hi[0] - lo[0]); s.x0 = half * (hi[0] + lo[0]);
+    s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
+    s.w0 = num<T>::half_pi();
+    sm2_carve<T, false>(s, reinterpret_cast<T*>(fts_dyn_smem), a.n);
+    sm2_stage<T, false>(s, &a.grid->x, &a.grid->w, nullptr, 2, a.n);
+    __syncthreads();
+    T acc = level_sum_2d<T, F, false>(s, p, a.n, 0, true, tid, blockDim.x);
+    if (tid == 0) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
+    const Comp<T> tot = block_reduce(comp_of(acc), red);
+    if (tid == 0) a.value[b] = s.dx * s.dy * (a.h * a.h) * tot.value();
+}
+
+// ------------------------------------------------------------------------------------ 3D -----
+template <class T> struct Sm3 {
+    T *xp, *xm, *yp, *ym, *zp, *zm, *w;
+    T dx, x0, dy, y0, dz, z0, w0;
+};
+
+template <class T> __device__ __forceinline__ void sm3_carve(Sm3<T>& s, T* base, int n)
+{
+    s.xp = base; s.xm = base + n; s.yp = base + 2 * n; s.ym = base + 3 * n; s.zp = base + 4 * n; s.zm = base + 5 * n; s.w = base + 6 * n;
+}
+
+// the reference's coordinate hoist (adaptive.jl:570-580), into shared memory
+template <class T> __device__ __forceinline__ void sm3_stage(Sm3<T>& s, const T* x, const T* w, int stride, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const T xi = x[(size_t)i * stride];
+        s.xp[i] = fm::fma(s.dx, xi, s.x0);
+        s.xm[i] = fm::fma(-s.dx, xi, s.x0);
+        s.yp[i] = fm::fma(s.dy, xi, s.y0);
+        s.ym[i] = fm::fma(-s.dy, xi, s.y0);
+        s.zp[i] = fm::fma(s.dz, xi, s.z0);
+        s.zm[i] = fm::fma(-s.dz, xi, s.z0);
+        s.w[i] = w[(size_t)i * stride];
+    }
+}
+
+#define FTS_FE(X, Y, Z) F::template eval<T, true>(X, Y, Z, p)
+template <class T, class F> __device__ __forceinline__ T cell3(const Sm3<T>& s, const T* p, int i, int j, int k)
+{
+    const T xp = s.xp[i], xm = s.xm[i], yp = s.yp[j], ym = s.ym[j], zp = s.zp[k], zm = s.zm[k];
+    const T f = ((FTS_FE(xp, yp, zp) + FTS_FE(xm, yp, zp)) + (FTS_FE(xp, ym, zp) + FTS_FE(xm, ym, zp))) +
+                ((FTS_FE(xp, yp, zm) + FTS_FE(xm, yp, zm)) + (FTS_FE(xp, ym, zm) + FTS_FE(xm, ym, zm)));
+    return (s.w[i] * s.w[j] * s.w[k]) * f;
+}
+template <class T, class F> __device__ __forceinline__ T plane3(const Sm3<T>& s, const T* p, int i, int j)
+{
+    const T x0 = s.x0, y0 = s.y0, z0 = s.z0;
+    const T xp = s.xp[i], xm = s.xm[i], ypi = s.yp[i], ymi = s.ym[i];
+    const T ypj = s.yp[j], ymj = s.ym[j], zpj = s.zp[j], zmj = s.zm[j];
+    const T f = ((FTS_FE(xp, ypj, z0) + FTS_FE(xm, ypj, z0)) + (FTS_FE(xp, ymj, z0) + FTS_FE(xm, ymj, z0))) +
+                ((FTS_FE(xp, y0, zpj) + FTS_FE(xm, y0, zpj)) + (FTS_FE(xp, y0, zmj) + FTS_FE(xm, y0, zmj))) +
+                ((FTS_FE(x0, ypi, zpj) + FTS_FE(x0, ymi, zpj)) + (FTS_FE(x0, ypi, zmj) + FTS_FE(x0, ymi, zmj)));
+    return (s.w[i] * s.w[j] * s.w0) * f;
+}
+template <class T, class F> __device__ __forceinline__ T axis3(const Sm3<T>& s, const T* p, int i)
+{
+    const T x0 = s.x0, y0 = s.y0, z0 = s.z0;
+    const T f = (FTS_FE(s.xp[i], y0, z0) + FTS_FE(s.xm[i], y0, z0)) + (FTS_FE(x0, s.yp[i], z0) + FTS_FE(x0, s.ym[i], z0)) +
+                (FTS_FE(x0, y0, s.zp[i]) + FTS_FE(x0, y0, s.zm[i]));
+    return (s.w[i] * (s.w0 * s.w0)) * f;
+}
+#undef FTS_FE
+
+// New cells of a level in 0-based indices (adaptive.jl:430-456 / 585-690):
+//   class A  i even           : all (j,k) octants, planes(i,j) for all j, axes(i)
+//   class B  i odd, j even    : all k octants, planes(i,j)
+//   class C  i odd, j odd     : k even octants only
+template <class T, class F>
+__device__ __forceinline__ T level_sum_3d(const Sm3<T>& s, const T* p, int n, int log2n, bool all_new, long long start, long long stride)
+{
+    T acc = num<T>::zero();
+    if (all_new) {
+        const long long n2 = (long long)n * n, ncell = n2 * n;
+        for (long long t = start; t < ncell; t += stride) {
+            const int i = (int)(t / n2);
+            const int r = (int)(t - (long long)i * n2);
+            const int j = r / n, k = r - j * n;
+            acc = acc + cell3<T, F>(s, p, i, j, k);
+        }
+        for (long long t = start; t < n2; t += stride) {
+            const int i = (int)(t / n), j = (int)(t - (long long)i * n);
+            acc = acc + plane3<T, F>(s, p, i, j);
+        }
+        for (long long t = start; t < n; t += stride) acc = acc + axis3<T, F>(s, p, (int)t);
+    } else {
+        const int l2 = log2n;
+        const long long n3 = 1LL << (3 * l2);
+        const long long nA = n3 >> 1, nB = n3 >> 2, nC = n3 >> 3;
+        const long long ncell = nA + nB + nC;
+        for (long long t = start; t < ncell; t += stride) {
+            int i, j, k;
+            if (t < nA) {
+                i = (int)(t >> (2 * l2)) << 1;
+                j = (int)(t >> l2) & (n - 1);
+                k = (int)t & (n - 1);
+            } else if (t < nA + nB) {
+                const long long u = t - nA;
+                i = ((int)(u >> (2 * l2 - 1)) << 1) | 1;
+                const int r = (int)(u & ((1LL << (2 * l2 - 1)) - 1));
+                j = (r >> l2) << 1;
+                k = r & (n - 1);
+            } else {
+                const long long u = t - nA - nB;
+                i = ((int)(u >> (2 * l2 - 2)) << 1) | 1;
+                const int r = (int)(u & ((1LL << (2 * l2 - 2)) - 1));
+                j = ((r >> (l2 - 1)) << 1) | 1;
+                k = (r & ((n >> 1) - 1)) << 1;
+            }
+            acc = acc + cell3<T, F>(s, p, i, j, k);
+        }
+        const long long pA = ((long long)n * n) >> 1, nplane = pA + (pA >> 1);
+        for (long long t = start; t < nplane; t += stride) {
+            int i, j;
+            if (t < pA) {
+                i = (int)(t >> l2) << 1;
+                j = (int)(t & (n - 1));
+            } else {
+                const long long u = t - pA;
+                i = ((int)(u >> (l2 - 1)) << 1) | 1;
+                j = (int)(u & ((n >> 1) - 1)) << 1;
+            }
+            acc = acc + plane3<T, F>(s, p, i, j);
+        }
+        for (long long t = start; t < (n >> 1); t += stride) acc = acc + axis3<T, F>(s, p, (int)t << 1);
+    }
+    return acc;
+}
+
+// adaptive_integrate_3D_avx   adaptive.jl:489-706
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive3d_cta(const Args<T> a)
+{
+    __shared__ T red[64];
+    __shared__ int s_done;
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[3], hi[3];
+    bool neg;
+    int flags;
+    if (!load_box<3>(a, b, lo, hi, neg, flags)) {
+        if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        return;
+    }
+    const T half = num<T>::half();
+    Sm3<T> s;
+    s.dx = half * (hi[0] - lo[0]); s.x0 = half * (hi[0] + lo[0]);
+    s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
+    s.dz = half * (hi[2] - lo[2]); s.z0 = half * (hi[2] + lo[2]);
+    s.w0 = num<T>::half_pi();
+    const int nmax = a.max_levels > 0 ? (2 << a.max_levels) : 2;
+    sm3_carve<T>(s, reinterpret_cast<T*>(fts_dyn_smem), nmax);
+    T h = a.tm * half;
+    sm3_stage<T>(s, a.ix, a.iw, 1, 2);
+    __syncthreads();
+    T acc = level_sum_3d<T, F>(s, p, 2, 1, true, tid, blockDim.x);
+    if (tid == 0) acc = acc + (s.w0 * s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.z0, p);
+    Comp<T> s_total = block_reduce(comp_of(acc), red);
+    T old_res = s.dx * s.dy * s.dz * (h * h * h) * s_total.value();
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 2 << level;
+        const Node<T>* lv = a.nodes + (n - 4);
+        sm3_stage<T>(s, &lv->x, &lv->w, 2, n);
+        __syncthreads();
+        acc = level_sum_3d<T, F>(s, p, n, level + 1, false, tid, blockDim.x);
+        const Comp<T> lv_sum = block_reduce(comp_of(acc), red);
+        if (tid == 0) {
+            s_total.merge(lv_sum);
+            const T new_res = s.dx * s.dy * s.dz * (h * h * h) * s_total.value();
+            err = fm::abs(new_res - old_res);
+            old_res = new_res;
+            level_used = level;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            if (conv) flags |= FLAG_CONVERGED;
+            s_done = conv ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
+// integrate3D_avx   integrate3D.jl:68-123
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed3d_cta(const Args<T> a)
+{
+    __shared__ T red[64];
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T* lo = a.low + b * a.bstride;
+    const T* hi = a.up + b * a.bstride;
+    Sm3<T> s;
+    s.dx = half * (hi[0] - lo[0]); s.x0 = half * (hi[0] + lo[0]);
+    s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
+    s.dz = half * (hi[2] - lo[2]); s.z0 = half * (hi[2] + lo[2]);
+    s.w0 = num<T>::half_pi();
+    sm3_carve<T>(s, reinterpret_cast<T*>(fts_dyn_smem), a.n);
+    sm3_stage<T>(s, &a.grid->x, &a.grid->w, 2, a.n);
+    __syncthreads();
+    T acc = level_sum_3d<T, F>(s, p, a.n, 0, true, tid, blockDim.x);
+    if (tid == 0) acc = acc + (s.w0 * s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.z0, p);
+    const Comp<T> tot = block_reduce(comp_of(acc), red);
+    if (tid == 0) a.value[b] = (s.dx * s.dy * s.dz * (a.h * a.h * a.h)) * tot.value();
+}
+
+// ------------------------------------------------------------------ one level, whole grid ----
+// Partial sum of level `a.level` (0 = base grid) of ONE 2D/3D integral (bounds/params at index
+// 0), flat new-cell index dealt over gridDim.x CTAs and a.nranks devices.  The last CTA to
+// finish (ticket) merges the per-CTA (s,c) partials in CTA order and writes a.partial_out[0..1].
+template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS) k_level_grid(const Args<T> a)
+{
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    __shared__ T red[64];
+    __shared__ int s_last;
+    if (a.state && a.state[5] != num<T>::zero()) return;  // converged at an earlier level
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, 0);
+    const T half = num<T>::half();
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    const long long start = (long long)a.rank * gthreads + (long long)blockIdx.x * blockDim.x + tid;
+    const long long stride = gthreads * a.nranks;
+    const int level = a.level;
+    const int n = level == 0 ? 2 : (2 << level);
+    T acc;
+    if constexpr (D == 3) {
+        Sm3<T> s;
+        s.dx = half * (a.up[0] - a.low[0]); s.x0 = half * (a.up[0] + a.low[0]);
+        s.dy = half * (a.up[1] - a.low[1]); s.y0 = half * (a.up[1] + a.low[1]);
+        s.dz = half * (a.up[2] - a.low[2]); s.z0 = half * (a.up[2] + a.low[2]);
+        s.w0 = num<T>::half_pi();
+        sm3_carve<T>(s, reinterpret_cast<T*>(fts_dyn_smem), n);
+        if (level == 0) sm3_stage<T>(s, a.ix, a.iw, 1, 2);
+        else { const Node<T>* lv = a.nodes + (n - 4); sm3_stage<T>(s, &lv->x, &lv->w, 2, n); }
+        __syncthreads();
+        acc = level_sum_3d<T, F>(s, p, n, level + 1, level == 0, start, stride);
+        if (level == 0 && start == 0) acc = acc + (s.w0 * s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.z0, p);
+    } else {
+        Sm2<T> s;
+        s.dx = half * (a.up[0] - a.low[0]); s.x0 = half * (a.up[0] + a.low[0]);
+        s.dy = half * (a.up[1] - a.low[1]); s.y0 = half * (a.up[1] + a.low[1]);
+        s.w0 = num<T>::half_pi();
+        sm2_carve<T, CMPL>(s, reinterpret_cast<T*>(fts_dyn_smem), n);
+        if (level == 0) sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2);
+        else if constexpr (CMPL) { const NodeC<T>* lv = a.nodes_c + (n - 4); sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n); }
+        else { const Node<T>* lv = a.nodes + (n - 4); sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n); }
+        __syncthreads();
+        acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, level == 0, start, stride);
+        if (level == 0 && start == 0) {
+            if constexpr (CMPL) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.dx, s.dx, s.dy, s.dy, p);
+            else {
+                if constexpr (D == 2) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
+            }
+        }
+    }
+    const Comp<T> bsum = block_reduce(comp_of(acc), red);
+    if (tid == 0) {
+        a.block_partials[2 * blockIdx.x] = bsum.s;
+        a.block_partials[2 * blockIdx.x + 1] = bsum.c;
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Comp<T> tot;
+    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+        Comp<T> o;
+        o.s = __ldcg(a.block_partials + 2 * i);
+        o.c = __ldcg(a.block_partials + 2 * i + 1);
+        tot.merge(o);
+    }
+    tot = block_reduce(tot, red);
+    if (tid == 0) {
+        a.partial_out[0] = tot.s;
+        a.partial_out[1] = tot.c;
+        *a.ticket = 0u;
+    }
+}
+
+// Stop test after the partials of all ranks are known (adaptive.jl:693-700): one thread,
+// identical arithmetic on every rank.  partials = [nranks][2] (s, c) in rank order.
+// state = {s_total.s, s_total.c, old_res, value, err, done, level_used, h}
+// state[5] (done): 0 running, 1 converged, 2 zero-width box under the quad() edge rules.
+template <class T, int D> __global__ void k_sharded_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
+                                                         const T* partials, T* state, int options)
+{
+    if (level > 0 && state[5] != num<T>::zero()) return;
+    if (level == 0 && (options & OPT_QUAD_EDGE)) {  // any(low .== up) -> zero(T)   quad.jl:96-98,129-131
+        bool zero = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) zero = zero || (low[d] == up[d]);
+        if (zero) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) state[i] = num<T>::zero();
+            state[5] = num<T>::from_double(2.0);
+            return;
+        }
+    }
+    const T half = num<T>::half();
+    Comp<T> tot;
+    if (level > 0) {
+        tot.s = state[0];
+        tot.c = state[1];
+    }
+    for (int r = 0; r < nranks; ++r) {
+        Comp<T> o;
+        o.s = partials[2 * r];
+        o.c = partials[2 * r + 1];
+        tot.merge(o);
+    }
+    T scale = num<T>::one();
+#pragma unroll
+    for (int d = 0; d < D; ++d) scale = scale * (half * (up[d] - low[d]));
+    const T h = level == 0 ? tm * half : state[7] * half;
+    T hD = h;
+#pragma unroll
+    for (int d = 1; d < D; ++d) hD = hD * h;
+    const T res = scale * hD * tot.value();
+    state[0] = tot.s;
+    state[1] = tot.c;
+    state[7] = h;
+    state[6] = num<T>::from_double((double)level);
+    if (level == 0) {
+        state[2] = res;
+        state[3] = res;
+        state[4] = num<T>::zero();
+        state[5] = num<T>::zero();
+    } else {
+        const T err = fm::abs(res - state[2]);
+        state[2] = res;
+        state[3] = res;
+        state[4] = err;
+        if (err <= fm::err_target(res, rtol, atol)) state[5] = num<T>::one();
+    }
+}
+
+}  // namespace fts

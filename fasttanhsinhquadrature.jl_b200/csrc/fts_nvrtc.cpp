@@ -1,0 +1,209 @@
+// fts_nvrtc.cpp — user integrands: CUDA-C++ body -> NVRTC -> sm_100a cubin -> same kernel templates.
+//
+// The reference specialises and inlines an arbitrary Julia callable into its loops
+// (`f::F ... where F`, /root/reference/src/adaptive.jl:28).  A host closure cannot run on the
+// GPU, so the boundary takes the integrand as source: the body is wrapped into a functor with
+// the builtin-family protocol and the library's own kernel templates (fts_kernels.cuh, embedded
+// in this library at build time) are instantiated for it.  Compilation needs no GPU; the cubin is
+// loaded lazily on first launch.  Modules are cached by (body, kind, nparams).
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "fts_internal.h"
+
+using namespace fts_host;
+
+extern const char fts_src_math[];     // fts_math.cuh      (generated: build/fts_embedded_src.cpp)
+extern const char fts_src_kernels[];  // fts_kernels.cuh
+extern const char fts_src_cta[];      // fts_kernels_cta.cuh
+
+namespace {
+
+struct KernelSpec {
+    int dtype, kid, fast;
+    std::string expr;
+};
+
+struct Module {
+    std::vector<char> cubin;
+    std::vector<KernelSpec> specs;
+    std::vector<std::string> lowered;
+    cudaLibrary_t lib = nullptr;
+    bool loaded = false;
+    std::map<std::tuple<int, int, int>, const void*> kernels;
+    std::mutex mu;
+    int refs = 0;
+};
+
+std::mutex g_cache_mu;
+std::map<std::tuple<std::string, int, int>, Module*> g_cache;
+
+const char* kind_args(int kind)
+{
+    switch (kind) {
+    case FTS_KIND_1D: return "T x";
+    case FTS_KIND_2D: return "T x, T y";
+    case FTS_KIND_3D: return "T x, T y, T z";
+    case FTS_KIND_1D_CMPL: return "T x, T bmx, T xma";
+    case FTS_KIND_2D_CMPL: return "T x, T y, T bmx, T xma, T dmy, T ymc";
+    }
+    return nullptr;
+}
+
+void add_specs(std::vector<KernelSpec>& v, int kind)
+{
+    const char* tn[3] = {"float", "double", "fts::dd"};
+    const char *fixed = nullptr, *adapt = nullptr, *adapt_cta = nullptr, *fixed_cta = nullptr;
+    switch (kind) {
+    case FTS_KIND_1D: fixed = "k_fixed1d_tpi"; adapt = "k_adaptive1d_tpi"; adapt_cta = "k_adaptive1d_cta"; fixed_cta = "k_fixed1d_cta"; break;
+    case FTS_KIND_2D: fixed = "k_fixed2d_tpi"; adapt = "k_adaptive2d_tpi"; adapt_cta = "k_adaptive2d_cta"; fixed_cta = "k_fixed2d_cta"; break;
+    case FTS_KIND_3D: fixed = "k_fixed3d_tpi"; adapt = "k_adaptive3d_tpi"; adapt_cta = "k_adaptive3d_cta"; fixed_cta = "k_fixed3d_cta"; break;
+    case FTS_KIND_1D_CMPL: adapt = "k_adaptive1d_cmpl_tpi"; adapt_cta = "k_adaptive1d_cmpl_cta"; break;
+    case FTS_KIND_2D_CMPL: adapt = "k_adaptive2d_tpi"; adapt_cta = "k_adaptive2d_cta"; break;
+    }
+    const int ndt = (kind == FTS_KIND_1D || kind == FTS_KIND_1D_CMPL) ? 3 : 2;  // Double64: 1D kinds
+    for (int dt = 0; dt < ndt; ++dt) {
+        for (int fast = 0; fast < 2; ++fast) {
+            if (dt == FTS_DD64 && fast) continue;
+            const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") + ">";
+            if (fixed) v.push_back({dt, KID_FIXED_TPI, fast, std::string("fts::") + fixed + targs});
+            if (adapt) v.push_back({dt, KID_ADAPT_TPI, fast, std::string("fts::") + adapt + targs});
+        }
+        if (dt != FTS_DD64) {
+            const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand>";
+            if (adapt_cta) v.push_back({dt, KID_ADAPT_CTA, 1, std::string("fts::") + adapt_cta + targs});
+            if (fixed_cta) v.push_back({dt, KID_FIXED_CTA, 1, std::string("fts::") + fixed_cta + targs});
+            if (kind == FTS_KIND_2D || kind == FTS_KIND_2D_CMPL)
+                v.push_back({dt, KID_LEVEL_GRID, 1, std::string("fts::k_level_grid<") + tn[dt] + ", FtsUserIntegrand, 2>"});
+            if (kind == FTS_KIND_3D)
+                v.push_back({dt, KID_LEVEL_GRID, 1, std::string("fts::k_level_grid<") + tn[dt] + ", FtsUserIntegrand, 3>"});
+        }
+    }
+}
+
+int nvrtc_fail(nvrtcResult r, const char* what, nvrtcProgram prog, char* log, size_t loglen)
+{
+    std::string msg = std::string("NVRTC: ") + nvrtcGetErrorString(r) + " in " + what;
+    if (prog && log && loglen) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::vector<char> buf(n + 1, 0);
+        if (n) nvrtcGetProgramLog(prog, buf.data());
+        size_t m = n < loglen - 1 ? n : loglen - 1;
+        memcpy(log, buf.data(), m);
+        log[m] = 0;
+    }
+    return set_error(FTS_ERR_NVRTC, msg);
+}
+
+int compile(const std::string& body, int kind, int nparams, Module* m, char* log, size_t loglen)
+{
+    const char* args = kind_args(kind);
+    std::string src;
+    src += "#include \"fts_kernels.cuh\"\n#include \"fts_kernels_cta.cuh\"\n";
+    src += "struct FtsUserIntegrand {\n    static constexpr int NP = " + std::to_string(nparams) + ";\n";
+    src += std::string("    template <class T, bool FAST> static __device__ __forceinline__ T eval(") + args + ", const T* p)\n    {\n";
+    src += body;
+    src += "\n    }\n};\n";
+    if (kind == FTS_KIND_2D_CMPL) src += "namespace fts { template <> struct is_cmpl2d<FtsUserIntegrand> { static constexpr bool value = true; }; }\n";
+
+    const char* hdr_src[] = {fts_src_math, fts_src_kernels, fts_src_cta};
+    const char* hdr_name[] = {"fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh"};
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 3, hdr_src, hdr_name);
+    if (r != NVRTC_SUCCESS) return nvrtc_fail(r, "nvrtcCreateProgram", nullptr, log, loglen);
+    add_specs(m->specs, kind);
+    for (auto& s : m->specs) {
+        r = nvrtcAddNameExpression(prog, s.expr.c_str());
+        if (r != NVRTC_SUCCESS) { nvrtc_fail(r, "nvrtcAddNameExpression", prog, log, loglen); nvrtcDestroyProgram(&prog); return FTS_ERR_NVRTC; }
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
+    r = nvrtcCompileProgram(prog, 5, opts);
+    if (r != NVRTC_SUCCESS) { nvrtc_fail(r, "nvrtcCompileProgram", prog, log, loglen); nvrtcDestroyProgram(&prog); return FTS_ERR_NVRTC; }
+    for (auto& s : m->specs) {
+        const char* low = nullptr;
+        r = nvrtcGetLoweredName(prog, s.expr.c_str(), &low);
+        if (r != NVRTC_SUCCESS) { nvrtc_fail(r, "nvrtcGetLoweredName", prog, log, loglen); nvrtcDestroyProgram(&prog); return FTS_ERR_NVRTC; }
+        m->lowered.push_back(low);
+    }
+    size_t n = 0;
+    r = nvrtcGetCUBINSize(prog, &n);
+    if (r != NVRTC_SUCCESS || n == 0) { nvrtc_fail(r, "nvrtcGetCUBINSize", prog, log, loglen); nvrtcDestroyProgram(&prog); return FTS_ERR_NVRTC; }
+    m->cubin.resize(n);
+    r = nvrtcGetCUBIN(prog, m->cubin.data());
+    nvrtcDestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS) return nvrtc_fail(r, "nvrtcGetCUBIN", nullptr, log, loglen);
+    if (log && loglen) log[0] = 0;
+    return FTS_OK;
+}
+
+}  // namespace
+
+// used by fts_host.cu
+const void* fts_nvrtc_kernel(void* module, int dtype, int kid, int fast)
+{
+    Module* m = (Module*)module;
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (!m->loaded) {
+        cudaError_t e = cudaLibraryLoadData(&m->lib, m->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e != cudaSuccess) { cuda_error(e, "cudaLibraryLoadData(user integrand cubin)"); return nullptr; }
+        for (size_t i = 0; i < m->specs.size(); ++i) {
+            cudaKernel_t k = nullptr;
+            e = cudaLibraryGetKernel(&k, m->lib, m->lowered[i].c_str());
+            if (e != cudaSuccess) { cuda_error(e, "cudaLibraryGetKernel"); return nullptr; }
+            m->kernels[std::make_tuple(m->specs[i].dtype, m->specs[i].kid, m->specs[i].fast)] = (const void*)k;
+        }
+        m->loaded = true;
+    }
+    auto it = m->kernels.find(std::make_tuple(dtype, kid, fast));
+    return it == m->kernels.end() ? nullptr : it->second;
+}
+
+void fts_nvrtc_release(void* module)
+{
+    // modules stay in the process-wide cache (compiled once per distinct source)
+    (void)module;
+}
+
+extern "C" int fts_integrand_nvrtc(const char* body, int kind, int nparams, fts_integrand* out, char* log, size_t loglen)
+{
+    if (!body || !out || !kind_args(kind) || nparams < 0 || nparams > 64)
+        return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_integrand_nvrtc: bad arguments");
+    Module* m = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto key = std::make_tuple(std::string(body), kind, nparams);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) {
+            m = it->second;
+        } else {
+            m = new Module();
+            int rc = compile(body, kind, nparams, m, log, loglen);
+            if (rc) { delete m; return rc; }
+            g_cache[key] = m;
+        }
+        m->refs++;
+    }
+    fts_integrand_s* f = new fts_integrand_s();
+    f->builtin = 0; f->family = -1; f->kind = kind; f->nparams = nparams;
+    f->module = m;
+    *out = f;
+    return FTS_OK;
+}
+
+// size of the cubin of an NVRTC integrand (lets CPU-only tests check that compilation happened)
+extern "C" int fts_integrand_cubin_size(fts_integrand f, size_t* bytes, int* nkernels)
+{
+    if (!f || f->builtin || !f->module) return set_error(FTS_ERR_INVALID_ARGUMENT, "not an NVRTC integrand");
+    Module* m = (Module*)f->module;
+    if (bytes) *bytes = m->cubin.size();
+    if (nkernels) *nkernels = (int)m->specs.size();
+    return FTS_OK;
+}

@@ -167,6 +167,13 @@ int fts_cache1d_generate(int dtype, int max_levels, int complement, void* tm_out
    (level l holds ALL 2^(l+1) nodes at offset 2^(l+1)-4). */
 int fts_cache_tensor_generate(int dtype, int D, int max_levels, void* tm_out,
                               void* initial_x, void* initial_w, void* xs_flat, void* ws_flat);
+/* 2D tensor-complement tables (extension for BASELINE config C; NOT in the reference, whose
+   quad_cmpl is 1D only, quad.jl:298-318): nodes t=i*h_l as caches.jl:173-177 on the window
+   t_w_max(T,2) (core.jl:207-221 with D=2, so products of two weights/complements stay above
+   floatmin), plus complements as caches.jl:84.  f32/f64. */
+int fts_cache_tensor_cmpl_generate(int dtype, int max_levels, void* tm_out, void* initial_x,
+                                   void* initial_w, void* initial_c, void* xs_flat, void* ws_flat,
+                                   void* cs_flat);
 
 /* ---- table upload (exact node parity: the caller's own nodes are used verbatim) ------------ */
 /* (x,w,h) = tanhsinh(T,N)  — consumed by integrate{1,2,3}D[_avx] (integrate1D.jl:74-147 ...) */
@@ -183,6 +190,9 @@ int fts_cache1d_upload(int dtype, int kind, int max_levels, const void* tm,
 int fts_cache_tensor_upload(int dtype, int D, int max_levels, const void* tm,
                             const void* initial_x, const void* initial_w,
                             const void* xs_flat, const void* ws_flat, fts_cache* out);
+int fts_cache_tensor_cmpl_upload(int dtype, int max_levels, const void* tm, const void* initial_x,
+                                 const void* initial_w, const void* initial_c, const void* xs_flat,
+                                 const void* ws_flat, const void* cs_flat, fts_cache* out);
 /* length(cache.xs) (caches.jl:25-29 depth guard) and D (0 for 1D caches) */
 int fts_cache_info(fts_cache c, int* dtype, int* D, int* kind, int* max_levels);
 int fts_cache_free(fts_cache c);
@@ -197,6 +207,8 @@ int fts_integrand_builtin(int family, fts_integrand* out);
 int fts_integrand_nvrtc(const char* body, int kind, int nparams, fts_integrand* out,
                         char* log, size_t loglen);
 int fts_integrand_info(fts_integrand f, int* kind, int* nparams, int* is_builtin);
+/* cubin size / kernel count of an NVRTC integrand (compilation needs no GPU) */
+int fts_integrand_cubin_size(fts_integrand f, size_t* bytes, int* nkernels);
 int fts_integrand_free(fts_integrand f);
 
 /* ---- launches: fixed grids ----------------------------------------------------------------- */
@@ -233,22 +245,27 @@ int fts_adaptive_batch_dev(fts_cache c, fts_integrand f, int order, int options,
                            void* out_value, void* out_err, int32_t* out_levels, int32_t* out_flags,
                            void* stream);
 
-/* ---- launches: one large 3D/2D integral sharded over its outer node index ------------------- */
-/* Partial level sum of ONE adaptive 2D/3D integral for shard `rank` of `nranks`
- * (outer index i dealt cyclically; adaptive.jl:430-456 / 585-690 index classes).
- * level 0 = the base grid (adaptive.jl:406-418).  Writes the compensated partial
- * (hi, lo) as two doubles to the DEVICE buffer `partial_dev[2]` on `stream`.  The caller
- * sums partials over ranks (NCCL all-reduce of 2 doubles) and feeds fts_adaptive_sharded_step. */
+/* ---- launches: one large 2D/3D integral sharded over devices ------------------------------ */
+/* Partial sum of refinement level `level` (0 = base grid, adaptive.jl:406-418; >=1 = the new
+ * points of adaptive.jl:430-456 / 585-690) of ONE adaptive 2D/3D integral for shard `rank` of
+ * `nranks`: the flat index over the level's new cells is dealt cyclically over ranks x CTAs
+ * (equal work per rank whatever the odd/even class mix).  low/up/params are DEVICE pointers to one
+ * box / one parameter row.  Writes the compensated partial (s, c) — two dtype elements — to the
+ * DEVICE buffer `partial_dev` on `stream`.  If `state_dev` is non-null and says "converged" the
+ * launch exits immediately, so all levels can be queued without a host round trip.
+ * The caller exchanges the partials of all ranks (NCCL all-gather of 2 elements) and calls
+ * fts_adaptive_sharded_step_dev. */
 int fts_adaptive_sharded_level_dev(fts_cache c, fts_integrand f,
                                    const void* low, const void* up, const void* params,
                                    int level, int rank, int nranks,
-                                   double* partial_dev, void* stream);
-/* Device-side stop test after the all-reduce (adaptive.jl:458-465): state_dev[8] doubles =
- * {s_total_hi, s_total_lo, old_res, new_res, err, done, level_used, h}; identical arithmetic
- * on every rank.  Kernels of later levels early-exit once done != 0. */
+                                   void* partial_dev, const void* state_dev, void* stream);
+/* Stop test after the exchange (adaptive.jl:458-465 / 693-700), one device thread, identical
+ * arithmetic on every rank.  partials_dev = [nranks][2] in rank order; state_dev = 8 dtype
+ * elements {s_total.s, s_total.c, old_res, value, err_est, done, level_used, h}
+ * (done: 0 running, 1 converged). */
 int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up,
-                                  const void* rtol, const void* atol, int level,
-                                  const double* partial_dev, double* state_dev, void* stream);
+                                  const void* rtol, const void* atol, int level, int nranks,
+                                  const void* partials_dev, void* state_dev, void* stream);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Register-resident DFMA (dtype FTS_F64) / FFMA (FTS_F32) chain microbenchmark: the measured

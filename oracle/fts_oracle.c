@@ -131,25 +131,45 @@ int fts_or_num_threads(void)
 #endif
 }
 
-void fts_or_batch_adaptive1d_f64(int fam, const double* params, int pstride, const double* low,
-                                 const double* up, int bstride, double rtol, double atol,
-                                 int max_levels, double tm, const double* ix, const double* iw,
-                                 const double* xs, const double* ws, long batch, double* value,
-                                 double* err, int* level, int* conv, long* evals, int nthreads)
+/* Julia specialises and inlines the integrand into adaptive_integrate_1D (`f::F ... where F`,
+ * adaptive.jl:28); the per-family bodies below give gcc the same chance (constant family id +
+ * flatten), so the CPU baseline is not handicapped by the oracle's run-time family switch. */
+#define OR_BATCH1D_BODY(FAMCONST)                                                                  \
+    for (long b = 0; b < batch; ++b) {                                                             \
+        fts_or_result_f64 r;                                                                       \
+        fts_or_adaptive1d_f64(FAMCONST, params + b * pstride, NULL, low[b * bstride],              \
+                              up[b * bstride], rtol, atol, max_levels, tm, ix, iw, xs, ws, &r);    \
+        value[b] = r.value;                                                                        \
+        if (err) err[b] = r.err;                                                                   \
+        if (level) level[b] = r.level;                                                             \
+        if (conv) conv[b] = r.converged;                                                           \
+        if (evals) evals[b] = r.evals;                                                             \
+    }
+
+__attribute__((flatten)) void fts_or_batch_adaptive1d_f64(
+    int fam, const double* params, int pstride, const double* low, const double* up, int bstride,
+    double rtol, double atol, int max_levels, double tm, const double* ix, const double* iw,
+    const double* xs, const double* ws, long batch, double* value, double* err, int* level,
+    int* conv, long* evals, int nthreads)
 {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    if (fam == FTS_F1_GAUSS) {
+#ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1024)
 #endif
-    for (long b = 0; b < batch; ++b) {
-        fts_or_result_f64 r;
-        fts_or_adaptive1d_f64(fam, params + b * pstride, NULL, low[b * bstride], up[b * bstride],
-                              rtol, atol, max_levels, tm, ix, iw, xs, ws, &r);
-        value[b] = r.value;
-        if (err) err[b] = r.err;
-        if (level) level[b] = r.level;
-        if (conv) conv[b] = r.converged;
-        if (evals) evals[b] = r.evals;
+        OR_BATCH1D_BODY(FTS_F1_GAUSS)
+    } else if (fam == FTS_F1_EXP) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024)
+#endif
+        OR_BATCH1D_BODY(FTS_F1_EXP)
+    } else {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024)
+#endif
+        OR_BATCH1D_BODY(fam)
     }
 }
 
