@@ -20,6 +20,7 @@
 
 using namespace fts_host;
 
+extern const char fts_src_dd[];       // fts_dd.cuh
 extern const char fts_src_math[];     // fts_math.cuh      (generated: build/fts_embedded_src.cpp)
 extern const char fts_src_kernels[];  // fts_kernels.cuh
 extern const char fts_src_cta[];      // fts_kernels_cta.cuh
@@ -31,12 +32,19 @@ struct KernelSpec {
     std::string expr;
 };
 
-struct Module {
+struct Program {  // one NVRTC compilation unit
     std::vector<char> cubin;
     std::vector<KernelSpec> specs;
     std::vector<std::string> lowered;
     cudaLibrary_t lib = nullptr;
-    bool loaded = false;
+    bool compiled = false, loaded = false;
+};
+
+struct Module {
+    std::string body;
+    int kind = 0, nparams = 0;
+    Program base;  // float + double kernels, compiled when the integrand is created
+    Program dd;    // Double64 kernels, compiled on first use (bodies may use functions without a dd overload)
     std::map<std::tuple<int, int, int>, const void*> kernels;
     std::mutex mu;
     int refs = 0;
@@ -57,7 +65,7 @@ const char* kind_args(int kind)
     return nullptr;
 }
 
-void add_specs(std::vector<KernelSpec>& v, int kind)
+void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
 {
     const char* tn[3] = {"float", "double", "fts::dd"};
     const char *fixed = nullptr, *adapt = nullptr, *adapt_cta = nullptr, *fixed_cta = nullptr;
@@ -70,6 +78,7 @@ void add_specs(std::vector<KernelSpec>& v, int kind)
     }
     const int ndt = (kind == FTS_KIND_1D || kind == FTS_KIND_1D_CMPL) ? 3 : 2;  // Double64: 1D kinds
     for (int dt = 0; dt < ndt; ++dt) {
+        if ((dt == FTS_DD64) != want_dd) continue;
         for (int fast = 0; fast < 2; ++fast) {
             if (dt == FTS_DD64 && fast) continue;
             const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") + ">";
@@ -103,7 +112,7 @@ int nvrtc_fail(nvrtcResult r, const char* what, nvrtcProgram prog, char* log, si
     return set_error(FTS_ERR_NVRTC, msg);
 }
 
-int compile(const std::string& body, int kind, int nparams, Module* m, char* log, size_t loglen)
+int compile(const std::string& body, int kind, int nparams, Program* m, bool want_dd, char* log, size_t loglen)
 {
     const char* args = kind_args(kind);
     std::string src;
@@ -114,12 +123,12 @@ int compile(const std::string& body, int kind, int nparams, Module* m, char* log
     src += "\n    }\n};\n";
     if (kind == FTS_KIND_2D_CMPL) src += "namespace fts { template <> struct is_cmpl2d<FtsUserIntegrand> { static constexpr bool value = true; }; }\n";
 
-    const char* hdr_src[] = {fts_src_math, fts_src_kernels, fts_src_cta};
-    const char* hdr_name[] = {"fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh"};
+    const char* hdr_src[] = {fts_src_dd, fts_src_math, fts_src_kernels, fts_src_cta};
+    const char* hdr_name[] = {"fts_dd.cuh", "fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh"};
     nvrtcProgram prog = nullptr;
-    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 3, hdr_src, hdr_name);
+    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 4, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) return nvrtc_fail(r, "nvrtcCreateProgram", nullptr, log, loglen);
-    add_specs(m->specs, kind);
+    add_specs(m->specs, kind, want_dd);
     for (auto& s : m->specs) {
         r = nvrtcAddNameExpression(prog, s.expr.c_str());
         if (r != NVRTC_SUCCESS) { nvrtc_fail(r, "nvrtcAddNameExpression", prog, log, loglen); nvrtcDestroyProgram(&prog); return FTS_ERR_NVRTC; }
@@ -141,7 +150,23 @@ int compile(const std::string& body, int kind, int nparams, Module* m, char* log
     nvrtcDestroyProgram(&prog);
     if (r != NVRTC_SUCCESS) return nvrtc_fail(r, "nvrtcGetCUBIN", nullptr, log, loglen);
     if (log && loglen) log[0] = 0;
+    m->compiled = true;
     return FTS_OK;
+}
+
+bool load_program(Module* m, Program* pr)
+{
+    if (pr->loaded) return true;
+    cudaError_t e = cudaLibraryLoadData(&pr->lib, pr->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) { cuda_error(e, "cudaLibraryLoadData(user integrand cubin)"); return false; }
+    for (size_t i = 0; i < pr->specs.size(); ++i) {
+        cudaKernel_t k = nullptr;
+        e = cudaLibraryGetKernel(&k, pr->lib, pr->lowered[i].c_str());
+        if (e != cudaSuccess) { cuda_error(e, "cudaLibraryGetKernel"); return false; }
+        m->kernels[std::make_tuple(pr->specs[i].dtype, pr->specs[i].kid, pr->specs[i].fast)] = (const void*)k;
+    }
+    pr->loaded = true;
+    return true;
 }
 
 }  // namespace
@@ -151,18 +176,17 @@ const void* fts_nvrtc_kernel(void* module, int dtype, int kid, int fast)
 {
     Module* m = (Module*)module;
     std::lock_guard<std::mutex> lk(m->mu);
-    if (!m->loaded) {
-        cudaError_t e = cudaLibraryLoadData(&m->lib, m->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-        if (e != cudaSuccess) { cuda_error(e, "cudaLibraryLoadData(user integrand cubin)"); return nullptr; }
-        for (size_t i = 0; i < m->specs.size(); ++i) {
-            cudaKernel_t k = nullptr;
-            e = cudaLibraryGetKernel(&k, m->lib, m->lowered[i].c_str());
-            if (e != cudaSuccess) { cuda_error(e, "cudaLibraryGetKernel"); return nullptr; }
-            m->kernels[std::make_tuple(m->specs[i].dtype, m->specs[i].kid, m->specs[i].fast)] = (const void*)k;
+    Program* pr = dtype == FTS_DD64 ? &m->dd : &m->base;
+    if (!pr->compiled) {
+        char log[4096];
+        if (compile(m->body, m->kind, m->nparams, pr, dtype == FTS_DD64, log, sizeof log)) {
+            set_error(FTS_ERR_NVRTC, std::string("Double64 instantiation of the user integrand failed to compile:\n") + log);
+            return nullptr;
         }
-        m->loaded = true;
     }
+    if (!load_program(m, pr)) return nullptr;
     auto it = m->kernels.find(std::make_tuple(dtype, kid, fast));
+    if (it == m->kernels.end()) set_error(FTS_ERR_UNSUPPORTED, "no kernel of this style for the user integrand / dtype");
     return it == m->kernels.end() ? nullptr : it->second;
 }
 
@@ -185,7 +209,8 @@ extern "C" int fts_integrand_nvrtc(const char* body, int kind, int nparams, fts_
             m = it->second;
         } else {
             m = new Module();
-            int rc = compile(body, kind, nparams, m, log, loglen);
+            m->body = body; m->kind = kind; m->nparams = nparams;
+            int rc = compile(body, kind, nparams, &m->base, false, log, loglen);
             if (rc) { delete m; return rc; }
             g_cache[key] = m;
         }
@@ -203,7 +228,7 @@ extern "C" int fts_integrand_cubin_size(fts_integrand f, size_t* bytes, int* nke
 {
     if (!f || f->builtin || !f->module) return set_error(FTS_ERR_INVALID_ARGUMENT, "not an NVRTC integrand");
     Module* m = (Module*)f->module;
-    if (bytes) *bytes = m->cubin.size();
-    if (nkernels) *nkernels = (int)m->specs.size();
+    if (bytes) *bytes = m->base.cubin.size();
+    if (nkernels) *nkernels = (int)m->base.specs.size();
     return FTS_OK;
 }

@@ -1,0 +1,135 @@
+"""Multi-GPU paths (one process per GPU, torch.distributed for the plumbing).
+
+The reference has no parallelism beyond SIMD lanes; the two decompositions below are
+what BASELINE.json's north_star asks for:
+
+* :func:`shard_range` / :func:`quad_sharded` — a batch of independent integrals is cut into
+  contiguous slices, one per rank.  There is NO data-path collective: each rank integrates its
+  slice; results are gathered only if the caller asks for the full vector.
+* :func:`adaptive_integrate_sharded` — ONE large 2D/3D adaptive integral: every rank sums its
+  share of a level's new cells (flat cell index dealt cyclically over ranks x CTAs), the ranks
+  exchange their compensated (s, c) partials with an all-gather of 2 elements, and each rank
+  evaluates the same stop test on the device (adaptive.jl:693-700).  All levels are queued
+  without a host round trip; launches after convergence exit immediately.
+
+The orchestration takes its two device steps as callables so that the CPU (gloo, world_size 2)
+tests can drive exactly this code with a CPU stand-in for the kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import api
+from . import _lib as L
+
+
+def shard_range(batch: int, rank: int, world: int) -> tuple:
+    """contiguous slice [start, stop) of `batch` items owned by `rank` (sizes differ by <= 1)"""
+    base, rem = divmod(batch, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def quad_sharded(f, low, up, *, params=None, gather: bool = True, group=None, **kw):
+    """`quad` over a batch sharded across the ranks of `group` (contiguous slices, no data-path
+    collective).  Returns the full result vector on every rank when gather=True, else the local
+    slice and its (start, stop)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    low_a, up_a = np.asarray(low), np.asarray(up)
+    dim = f.dim
+    batched_bounds = low_a.ndim == (1 if dim == 1 else 2)
+    p = None if params is None else np.asarray(params)
+    n = low_a.shape[0] if batched_bounds else (p.shape[0] if p is not None and p.ndim >= 1 else 1)
+    start, stop = shard_range(n, rank, world)
+    lo_l = low_a[start:stop] if batched_bounds else low
+    up_l = up_a[start:stop] if batched_bounds else up
+    p_l = p[start:stop] if (p is not None and p.ndim >= 1 and p.shape[0] == n) else params
+    local = np.atleast_1d(api.quad(f, lo_l, up_l, params=p_l, **kw)) if stop > start else np.zeros(0)
+    if not gather or world == 1:
+        return (local, (start, stop)) if not gather else local
+    sizes = [shard_range(n, r, world) for r in range(world)]
+    width = max(b - a for a, b in sizes)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    buf = torch.zeros(width, dtype=torch.float64, device=dev)
+    buf[: local.shape[0]] = torch.from_numpy(np.asarray(local, np.float64))
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    return np.concatenate([o[: b - a].cpu().numpy() for o, (a, b) in zip(out, sizes)])
+
+
+def run_sharded_levels(max_levels: int, rank: int, world: int, level_fn: Callable, step_fn: Callable, all_gather: Callable):
+    """The level loop shared by the GPU path and the CPU (gloo) tests.
+
+    level_fn(level, rank, world) -> this rank's partial of the level, a [2] tensor (s, c)
+    all_gather(partial)          -> [world, 2] tensor in rank order
+    step_fn(level, partials)     -> updates the state (stop test), returns nothing
+    No host synchronisation happens here."""
+    for level in range(max_levels + 1):
+        partial = level_fn(level, rank, world)
+        partials = all_gather(partial)
+        step_fn(level, partials)
+
+
+def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
+                               warn: bool = True):
+    """One large adaptive 2D/3D integral over all ranks of `group` (NCCL).  Returns an
+    AdaptiveResult with one element, identical on every rank."""
+    import torch
+    dist = _dist()
+    dt = api._dt(T)
+    if dt == api.Double64:
+        raise api.FtsError(L.ERR_UNSUPPORTED, "sharded integrals: float32/float64")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rtol_T, atol_T = api._resolve_tolerances(dt, rtol, atol)
+    dim = f.dim
+    if cache is None:
+        cache = api.adaptive_cache_3D(dt, max_levels=max_levels) if dim == 3 else api.adaptive_cache_2D(dt, max_levels=max_levels)
+    else:
+        api._require_cache_levels(cache, max_levels)
+    tdt = torch.float32 if dt == np.dtype(np.float32) else torch.float64
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lo = torch.tensor(np.asarray(low, dt), dtype=tdt, device=dev)
+    hi = torch.tensor(np.asarray(up, dt), dtype=tdt, device=dev)
+    p = torch.tensor(np.asarray(params, dt), dtype=tdt, device=dev) if (params is not None and f.nparams) else None
+    partial = torch.zeros(2, dtype=tdt, device=dev)
+    gathered = torch.zeros(world, 2, dtype=tdt, device=dev)
+    state = torch.zeros(8, dtype=tdt, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def level_fn(level, r, w):
+        api.sharded_level_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), params=p.data_ptr() if p is not None else 0, level=level,
+                              rank=r, nranks=w, partial=partial.data_ptr(), state=state.data_ptr(), stream=stream)
+        return partial
+
+    def all_gather(t):
+        if world == 1:
+            gathered.copy_(t.view(1, 2))
+        else:
+            dist.all_gather_into_tensor(gathered.view(-1), t, group=group)
+        return gathered
+
+    def step_fn(level, parts):
+        api.sharded_step_dev(cache, low=lo.data_ptr(), up=hi.data_ptr(), rtol=rtol_T[0], atol=atol_T[0], level=level, nranks=world,
+                             partials=parts.data_ptr(), state=state.data_ptr(), stream=stream)
+
+    run_sharded_levels(max_levels, rank, world, level_fn, step_fn, all_gather)
+    s = state.cpu().numpy()  # the only host synchronisation
+    conv = s[5] != 0
+    flags = np.array([L.FLAG_CONVERGED if conv else (L.FLAG_MAX_LEVELS if max_levels > 0 else 0)], np.int32)
+    res = api.AdaptiveResult(np.array([s[3]], dt), np.array([s[4]], dt), np.array([int(s[6])], np.int32), flags)
+    if warn and not conv and max_levels > 0 and rank == 0:
+        import warnings
+        warnings.warn(f"adaptive_integrate_{dim}D reached max_levels without meeting the requested tolerance. max_levels = {max_levels}, "
+                      f"estimated_error = {s[4]}, value = {s[3]}", api.ConvergenceWarning, stacklevel=2)
+    return res

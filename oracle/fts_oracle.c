@@ -277,6 +277,25 @@ void fts_or_batch_adaptive2d_f64(int fam, const double* params, int pstride, con
     }
 }
 
+/* Partial sum of one 3D refinement level for shard `rank` of `nranks` (outer index i dealt
+ * cyclically; level 0 = the base grid, owned by rank 0): the CPU stand-in used by the gloo
+ * world_size-2 tests of the multi-GPU orchestration (tests/test_distributed_cpu.py). */
+double fts_or_adaptive3d_level_partial_f64(int fam, const double* p, const double* low, const double* up,
+                                           const double* ix, const double* iw, const double* xs,
+                                           const double* ws, int level, int rank, int nranks)
+{
+    fts_or_fn_f64 f = {fam, p, NULL};
+    box3_f64 bx;
+    bx.dx = 0.5 * (up[0] - low[0]); bx.x0 = 0.5 * (up[0] + low[0]);
+    bx.dy = 0.5 * (up[1] - low[1]); bx.y0 = 0.5 * (up[1] + low[1]);
+    bx.dz = 0.5 * (up[2] - low[2]); bx.z0 = 0.5 * (up[2] + low[2]);
+    bx.w0 = M_PI / 2;
+    bx.w02 = bx.w0 * bx.w0;
+    if (level == 0) return rank == 0 ? fts_or_adaptive3d_level0_f64(&f, &bx, ix, iw) : 0.0;
+    long n = 2L << level, off = n - 4;
+    return fts_or_adaptive3d_level_sum_f64(&f, &bx, xs + off, ws + off, n, rank, nranks);
+}
+
 /* One 3D level sum with the outer index i split over OpenMP threads (BASELINE.md §3 plan for
  * the single large integral); partials are combined in thread order. */
 double fts_or_adaptive3d_level_sum_omp_f64(int fam, const double* p, const double* low,
