@@ -53,11 +53,21 @@ struct F1Poly7 {
 };
 struct F1Exp {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::exp(x); }
+    template <class T, bool FAST, int N> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N]) { exp_n<N>(x, f); }
 };
 struct F1Gauss {  // exp(-α*x^2)   README.md:102
     static constexpr int NP = 1;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p) { return fm::exp(-p[0] * (x * x)); }
+    template <class T, bool FAST, int N> static __device__ __forceinline__ void evaln(const T (&x)[N], const T* p, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = -p[0] * (x[i] * x[i]);
+        exp_n<N>(a, f);
+    }
 };
 struct F1Runge {  // 1/(1+25x^2)   benchmarks.jl:34
     static constexpr int NP = 1;

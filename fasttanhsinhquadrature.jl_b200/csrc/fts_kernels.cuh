@@ -64,6 +64,22 @@ template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP
     if (NP == 0) p[0] = num<T>::zero();
 }
 
+// Integrand evaluation at N independent points.  Families whose cost is one long dependent FP64
+// chain (exp) provide `evaln`, which interleaves the N chains (fts_math.cuh exp_n); every other
+// functor — NVRTC user bodies included — falls back to N scalar evaluations.
+template <class F, class = void> struct HasEvalN { static constexpr bool value = false; };
+template <class F> struct HasEvalN<F, decltype((void)F::HAS_EVALN)> { static constexpr bool value = F::HAS_EVALN; };
+
+template <class T, class F, bool FAST, int N> __device__ __forceinline__ void eval1d_n(const T (&x)[N], const T* p, T (&f)[N])
+{
+    if constexpr (HasEvalN<F>::value) {
+        F::template evaln<T, FAST, N>(x, p, f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], p);
+    }
+}
+
 template <class T> __device__ __forceinline__ Node<T> ldg_node(const Node<T>* p) { return *p; }
 template <> __device__ __forceinline__ Node<double> ldg_node<double>(const Node<double>* p)
 {
@@ -238,11 +254,15 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
     const T dx = half * (hi - lo), x0 = half * (hi + lo);
     T h = a.tm * half;
     const T w0 = num<T>::pi() * half;
-    T s_total = w0 * F::template eval<T, FAST>(x0, p);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const T xk = a.ix[i];
-        s_total = s_total + a.iw[i] * (F::template eval<T, FAST>(dx * xk + x0, p) + F::template eval<T, FAST>(x0 - dx * xk, p));
+    T s_total;
+    {   // level 0 (adaptive.jl:39-45): centre + the two initial node pairs, 5 evaluations in flight
+        const T d0 = dx * a.ix[0], d1 = dx * a.ix[1];
+        const T xs[5] = {x0, d0 + x0, x0 - d0, d1 + x0, x0 - d1};
+        T fs[5];
+        eval1d_n<T, F, FAST, 5>(xs, p, fs);
+        s_total = w0 * fs[0];
+        s_total = s_total + a.iw[0] * (fs[1] + fs[2]);
+        s_total = s_total + a.iw[1] * (fs[3] + fs[4]);
     }
     T old_res = dx * h * s_total;
     T err = num<T>::zero();
@@ -253,12 +273,17 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
         T s_new = num<T>::zero();
         const int n = 1 << level;
         const Node<T>* __restrict__ lv = nodes + (n - 2);
-#pragma unroll 2
-        for (int i = 0; i < n; ++i) {
-            const Node<T> nd = ldg_node(lv + i);
-            const T d = dx * nd.x;
-            const T xp = d + x0, xm = x0 - d;
-            s_new = muladd<T, FAST>(nd.w, F::template eval<T, FAST>(xp, p) + F::template eval<T, FAST>(xm, p), s_new);
+        // two node pairs per trip (n = 2^level is even): 4 independent evaluations in flight,
+        // accumulated in the reference's order
+#pragma unroll 1
+        for (int i = 0; i < n; i += 2) {
+            const Node<T> n0 = ldg_node(lv + i), n1 = ldg_node(lv + i + 1);
+            const T d0 = dx * n0.x, d1 = dx * n1.x;
+            const T xs[4] = {d0 + x0, x0 - d0, d1 + x0, x0 - d1};
+            T fs[4];
+            eval1d_n<T, F, FAST, 4>(xs, p, fs);
+            s_new = muladd<T, FAST>(n0.w, fs[0] + fs[1], s_new);
+            s_new = muladd<T, FAST>(n1.w, fs[2] + fs[3], s_new);
         }
         s_total = s_total + s_new;
         const T new_res = dx * h * s_total;
