@@ -31,6 +31,8 @@ bool g_inited = false;
 int g_device = -1;
 cudaDeviceProp g_prop;
 cudaStream_t g_stream = nullptr;  // internal stream of the host-buffer entry points
+cudaStream_t g_pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of fts_adaptive_batch
+cudaEvent_t g_pipe_ev = nullptr;
 
 std::vector<KernelEntry>& registry()
 {
@@ -173,9 +175,25 @@ extern "C" int fts_init(int device)
         // re-binding: drop per-device scratch
         for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
         if (g_stream) cudaStreamDestroy(g_stream);
+        for (auto& ps : g_pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
+        if (g_pipe_ev) cudaEventDestroy(g_pipe_ev);
+        g_pipe_ev = nullptr;
         g_stream = nullptr;
     }
-    if (!g_stream) FTS_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    if (!g_stream) {
+        // stream-ordered scratch (cudaMallocAsync) must stay cached in the pool between calls:
+        // with the default release threshold (0) every synchronisation returns it to the OS and
+        // the next launch pays milliseconds to get it back
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        FTS_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+        for (auto& ps : g_pipe) FTS_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+        FTS_CUDA(cudaEventCreateWithFlags(&g_pipe_ev, cudaEventDisableTiming));
+    }
     g_device = device;
     g_inited = true;
     return FTS_OK;
@@ -187,6 +205,9 @@ extern "C" int fts_shutdown(void)
     if (!g_inited) return FTS_OK;
     for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
     if (g_stream) cudaStreamDestroy(g_stream);
+    for (auto& ps : g_pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
+    if (g_pipe_ev) cudaEventDestroy(g_pipe_ev);
+    g_pipe_ev = nullptr;
     g_stream = nullptr;
     g_inited = false;
     return FTS_OK;
@@ -678,6 +699,38 @@ static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int o
     return FTS_OK;
 }
 
+// Persistent per-stream queue of the deep-level hand-off: {count, ticket, idx[capacity]}.  Launches
+// on one stream are ordered, so they can share a queue (the tail kernel re-arms it when it leaves);
+// different streams get different queues.
+struct TailQueue { int* buf = nullptr; size_t cap = 0; };
+static std::mutex g_tail_mu;
+static std::vector<std::pair<cudaStream_t, TailQueue>> g_tail_queues;
+static int tail_queue_for(cudaStream_t s, size_t batch, int** out)
+{
+    std::lock_guard<std::mutex> lk(g_tail_mu);
+    TailQueue* q = nullptr;
+    for (auto& e : g_tail_queues)
+        if (e.first == s) q = &e.second;
+    if (!q) {
+        g_tail_queues.emplace_back(s, TailQueue());
+        q = &g_tail_queues.back().second;
+    }
+    if (q->cap < batch) {
+        if (q->buf) {
+            FTS_CUDA(cudaStreamSynchronize(s));
+            FTS_CUDA(cudaFree(q->buf));
+            q->buf = nullptr;
+            q->cap = 0;
+        }
+        const size_t cap = batch + batch / 4 + 1024;
+        FTS_CUDA(cudaMalloc((void**)&q->buf, sizeof(int) * (cap + 2)));
+        FTS_CUDA(cudaMemset(q->buf, 0, sizeof(int) * 2));
+        q->cap = cap;
+    }
+    *out = q->buf;
+    return FTS_OK;
+}
+
 template <class T>
 static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, const void* low, const void* up, int bstride,
                         const void* params, int pstride, const void* rtol, const void* atol, int max_levels, long long batch,
@@ -712,7 +765,26 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     const int fast = order == FTS_ORDER_FAST ? 1 : 0;
     const void* fn = integrand_kernel(f, c->dtype, KID_ADAPT_TPI, fast);
     if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no adaptive kernel built for this integrand/dtype/order");
-    return launch(fn, batch, dim == 1 ? 256 : 128, &a, s);
+    // 1D: integrals still unconverged after `tail_level` are finished by one CTA each
+    // (k_adaptive1d_tail, same summation order) instead of stalling their warp for 2^level steps
+    const int tail_level = is_dd ? 7 : 8;
+    const void* fn_tail = (dim == 1 && max_levels > tail_level) ? integrand_kernel(f, c->dtype, KID_ADAPT_TAIL, fast) : nullptr;
+    a.tail_level = -1;
+    if (fn_tail) {
+        if (batch > 0x7fffffffLL) return set_error(FTS_ERR_INVALID_ARGUMENT, "batch too large for one launch");
+        int* queue = nullptr;
+        if (int rc = tail_queue_for(s, (size_t)batch, &queue)) return rc;
+        a.tail_level = tail_level;
+        a.tail_count = queue;
+        a.ticket = (unsigned int*)(queue + 1);
+        a.tail_idx = queue + 2;
+    }
+    if (int rc = launch(fn, batch, dim == 1 ? 256 : 128, &a, s)) return rc;
+    if (fn_tail) {
+        const long long cap = (long long)g_prop.multiProcessorCount * 8;
+        if (int rc = launch_raw(fn_tail, (unsigned)(batch < cap ? batch : cap), 256, 0, &a, s)) return rc;
+    }
+    return FTS_OK;
 }
 
 static int check_cache_match(fts_cache c, fts_integrand f)
@@ -758,6 +830,11 @@ extern "C" int fts_adaptive_batch_dev(fts_cache c, fts_integrand f, int order, i
     return set_error(FTS_ERR_INTERNAL, "bad dtype");
 }
 
+// Host-buffer entry point.  Large batches are cut into chunks that flow through a 3-stream
+// pipeline (H2D of chunk i+1 | kernel of chunk i | D2H of chunk i-1): PCIe is full duplex and the
+// integrals are independent, so the copies hide behind the kernel when the caller's buffers are
+// pinned (fts_host_alloc / cudaHostRegister).  Pageable buffers still work (the copies then stage
+// through the driver).
 extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int options, const void* low, const void* up,
                                   int bounds_stride, const void* params, int params_stride, const void* rtol, const void* atol,
                                   int max_levels, int64_t batch, void* out_value, void* out_err, int32_t* out_levels, int32_t* out_flags)
@@ -768,23 +845,50 @@ extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int o
     const int dim = kind_dim(f->kind);
     const size_t nb = bounds_stride ? (size_t)batch * bounds_stride : (size_t)dim;
     const size_t np = f->nparams ? (params_stride ? (size_t)batch * params_stride : (size_t)f->nparams) : 0;
-    void *dl, *du, *dp, *dv, *de, *dlv, *dfl;
-    if (int rc = stage_in(S_LOW, low, nb * es, &dl)) return rc;
-    if (int rc = stage_in(S_UP, up, nb * es, &du)) return rc;
-    if (int rc = stage_in(S_PAR, params, np * es, &dp)) return rc;
-    if (int rc = stage_out(S_VAL, true, (size_t)batch * es, &dv)) return rc;
-    if (int rc = stage_out(S_ERR, out_err != nullptr, (size_t)batch * es, &de)) return rc;
-    if (int rc = stage_out(S_LVL, out_levels != nullptr, (size_t)batch * 4, &dlv)) return rc;
-    if (int rc = stage_out(S_FLG, out_flags != nullptr, (size_t)batch * 4, &dfl)) return rc;
-    if (int rc = fts_adaptive_batch_dev(c, f, order, options, dl, du, bounds_stride, dp, params_stride, rtol, atol, max_levels, batch,
-                                        dv, de, (int32_t*)dlv, (int32_t*)dfl, g_stream))
-        return rc;
-    if (batch) {
-        FTS_CUDA(cudaMemcpyAsync(out_value, dv, (size_t)batch * es, cudaMemcpyDeviceToHost, g_stream));
-        if (out_err) FTS_CUDA(cudaMemcpyAsync(out_err, de, (size_t)batch * es, cudaMemcpyDeviceToHost, g_stream));
-        if (out_levels) FTS_CUDA(cudaMemcpyAsync(out_levels, dlv, (size_t)batch * 4, cudaMemcpyDeviceToHost, g_stream));
-        if (out_flags) FTS_CUDA(cudaMemcpyAsync(out_flags, dfl, (size_t)batch * 4, cudaMemcpyDeviceToHost, g_stream));
+    FTS_CUDA(g_scratch[S_LOW].need(nb * es));
+    FTS_CUDA(g_scratch[S_UP].need(nb * es));
+    if (np) FTS_CUDA(g_scratch[S_PAR].need(np * es));
+    FTS_CUDA(g_scratch[S_VAL].need((size_t)batch * es));
+    if (out_err) FTS_CUDA(g_scratch[S_ERR].need((size_t)batch * es));
+    if (out_levels) FTS_CUDA(g_scratch[S_LVL].need((size_t)batch * 4));
+    if (out_flags) FTS_CUDA(g_scratch[S_FLG].need((size_t)batch * 4));
+    char* dl = (char*)g_scratch[S_LOW].p; char* du = (char*)g_scratch[S_UP].p; char* dp = np ? (char*)g_scratch[S_PAR].p : nullptr;
+    char* dv = (char*)g_scratch[S_VAL].p; char* de = out_err ? (char*)g_scratch[S_ERR].p : nullptr;
+    char* dlv = out_levels ? (char*)g_scratch[S_LVL].p : nullptr; char* dfl = out_flags ? (char*)g_scratch[S_FLG].p : nullptr;
+
+    const int64_t kMinChunk = 1 << 16;
+    int nch = 1;
+    if (dim == 1 || batch >= 8 * kMinChunk) nch = (int)(batch / kMinChunk < 8 ? batch / kMinChunk : 8);
+    if (nch < 1) nch = 1;
+    // broadcast operands go first on the main stream; the pipeline streams wait for them
+    if (!bounds_stride) {
+        FTS_CUDA(cudaMemcpyAsync(dl, low, nb * es, cudaMemcpyHostToDevice, g_stream));
+        FTS_CUDA(cudaMemcpyAsync(du, up, nb * es, cudaMemcpyHostToDevice, g_stream));
     }
+    if (np && !params_stride) FTS_CUDA(cudaMemcpyAsync(dp, params, np * es, cudaMemcpyHostToDevice, g_stream));
+    FTS_CUDA(cudaEventRecord(g_pipe_ev, g_stream));
+    for (int ch = 0; ch < nch; ++ch) {
+        cudaStream_t s = nch == 1 ? g_stream : g_pipe[ch % 3];
+        const int64_t b0 = batch * ch / nch, b1 = batch * (ch + 1) / nch, nbatch = b1 - b0;
+        if (nbatch == 0) continue;
+        if (nch > 1) FTS_CUDA(cudaStreamWaitEvent(s, g_pipe_ev, 0));
+        const size_t ob = bounds_stride ? (size_t)b0 * bounds_stride * es : 0, op = params_stride ? (size_t)b0 * params_stride * es : 0;
+        if (bounds_stride) {
+            FTS_CUDA(cudaMemcpyAsync(dl + ob, (const char*)low + ob, (size_t)nbatch * bounds_stride * es, cudaMemcpyHostToDevice, s));
+            FTS_CUDA(cudaMemcpyAsync(du + ob, (const char*)up + ob, (size_t)nbatch * bounds_stride * es, cudaMemcpyHostToDevice, s));
+        }
+        if (np && params_stride) FTS_CUDA(cudaMemcpyAsync(dp + op, (const char*)params + op, (size_t)nbatch * params_stride * es, cudaMemcpyHostToDevice, s));
+        if (int rc = fts_adaptive_batch_dev(c, f, order, options, dl + ob, du + ob, bounds_stride, dp ? dp + op : nullptr, params_stride, rtol, atol,
+                                            max_levels, nbatch, dv + (size_t)b0 * es, de ? de + (size_t)b0 * es : nullptr,
+                                            dlv ? (int32_t*)(dlv + (size_t)b0 * 4) : nullptr, dfl ? (int32_t*)(dfl + (size_t)b0 * 4) : nullptr, s))
+            return rc;
+        FTS_CUDA(cudaMemcpyAsync((char*)out_value + (size_t)b0 * es, dv + (size_t)b0 * es, (size_t)nbatch * es, cudaMemcpyDeviceToHost, s));
+        if (out_err) FTS_CUDA(cudaMemcpyAsync((char*)out_err + (size_t)b0 * es, de + (size_t)b0 * es, (size_t)nbatch * es, cudaMemcpyDeviceToHost, s));
+        if (out_levels) FTS_CUDA(cudaMemcpyAsync(out_levels + b0, dlv + (size_t)b0 * 4, (size_t)nbatch * 4, cudaMemcpyDeviceToHost, s));
+        if (out_flags) FTS_CUDA(cudaMemcpyAsync(out_flags + b0, dfl + (size_t)b0 * 4, (size_t)nbatch * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (nch > 1)
+        for (int k = 0; k < 3; ++k) FTS_CUDA(cudaStreamSynchronize(g_pipe[k]));
     FTS_CUDA(cudaStreamSynchronize(g_stream));
     return FTS_OK;
 }

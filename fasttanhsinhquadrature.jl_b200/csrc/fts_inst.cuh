@@ -26,6 +26,16 @@ struct Registrar {
     };                                                                                                       \
     static fts_host::Registrar k_reg_##FUNCTOR(k_entries_##FUNCTOR, 8);
 
+// deep-level tail kernels of the 1D thread-per-integral path (CMPL selects the complement form)
+#define FTS_REGISTER_TAIL(FAM, FUNCTOR, CMPL)                                                                        \
+    static const fts_host::KernelEntry k_tail_entries_##FUNCTOR[] = {                                               \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_TAIL, 0, FTS_KPTR(fts::k_adaptive1d_tail<float, fts::FUNCTOR, false, CMPL>)},   \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_TAIL, 1, FTS_KPTR(fts::k_adaptive1d_tail<float, fts::FUNCTOR, true, CMPL>)},    \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_TAIL, 0, FTS_KPTR(fts::k_adaptive1d_tail<double, fts::FUNCTOR, false, CMPL>)},  \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_TAIL, 1, FTS_KPTR(fts::k_adaptive1d_tail<double, fts::FUNCTOR, true, CMPL>)},   \
+    };                                                                                                               \
+    static fts_host::Registrar k_tail_reg_##FUNCTOR(k_tail_entries_##FUNCTOR, 4);
+
 // adaptive-only families (complement kinds have no exported fixed-grid entry point)
 #define FTS_REGISTER_ADAPT_ONLY(FAM, FUNCTOR, ...)                                                           \
     static const fts_host::KernelEntry k_entries_##FUNCTOR[] = {                                            \

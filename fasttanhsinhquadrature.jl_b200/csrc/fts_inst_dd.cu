@@ -5,14 +5,16 @@
     static const fts_host::KernelEntry k_dd_entries_##FUNCTOR[] = {                                         \
         {FAM, FTS_DD64, fts_host::KID_FIXED_TPI, 0, FTS_KPTR(fts::k_fixed1d_tpi<fts::dd, fts::FUNCTOR, false>)},   \
         {FAM, FTS_DD64, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::k_adaptive1d_tpi<fts::dd, fts::FUNCTOR, false>)}, \
+        {FAM, FTS_DD64, fts_host::KID_ADAPT_TAIL, 0, FTS_KPTR(fts::k_adaptive1d_tail<fts::dd, fts::FUNCTOR, false, false>)}, \
     };                                                                                                       \
-    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 2);
+    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 3);
 
 #define FTS_REGISTER_DD_C1(FAM, FUNCTOR)                                                                     \
     static const fts_host::KernelEntry k_dd_entries_##FUNCTOR[] = {                                         \
         {FAM, FTS_DD64, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::k_adaptive1d_cmpl_tpi<fts::dd, fts::FUNCTOR, false>)}, \
+        {FAM, FTS_DD64, fts_host::KID_ADAPT_TAIL, 0, FTS_KPTR(fts::k_adaptive1d_tail<fts::dd, fts::FUNCTOR, false, true>)}, \
     };                                                                                                       \
-    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 1);
+    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 2);
 
 FTS_REGISTER_DD_1D(FTS_F1_POLY7, F1Poly7)
 FTS_REGISTER_DD_1D(FTS_F1_EXP, F1Exp)

@@ -17,7 +17,8 @@ enum KernelId : int {
     KID_FIXED_CTA = 2,     // k_fixed*_cta                 CTA per integral (FAST only)
     KID_ADAPT_CTA = 3,     // k_adaptive*_cta              CTA per integral (FAST only)
     KID_LEVEL_GRID = 4,    // k_level*_grid                many CTAs per integral, one launch per level
-    KID_COUNT = 5
+    KID_ADAPT_TAIL = 5,    // k_adaptive1d_tail               deep levels of queued 1D integrals (reference order)
+    KID_COUNT = 6
 };
 
 struct KernelEntry {

@@ -20,6 +20,11 @@ namespace fts {
 enum : int { OPT_QUAD_EDGE = 1 };
 enum : int { FLAG_CONVERGED = 1, FLAG_MAX_LEVELS = 2, FLAG_ZERO_WIDTH = 4, FLAG_FLIPPED = 8 };
 
+#ifndef FTS_TPI_PAIRS
+#define FTS_TPI_PAIRS 4
+#endif
+constexpr int TPI_PAIRS = FTS_TPI_PAIRS;  // node pairs per loop trip of the thread-per-integral 1D kernels (levels >= 2)
+
 template <class T> struct Node { T x, w; };             // 1D / tensor tables, interleaved
 template <class T> struct NodeC { T x, w, c, pad; };    // complement tables
 
@@ -55,6 +60,12 @@ template <class T> struct Args {
     unsigned int* ticket; // last-CTA election
     T* partial_out;       // [2] this rank's (s, c) of the level
     const T* state;       // [8] see fts_adaptive_sharded_step_dev; state[5] != 0 -> already converged
+    // deep-level hand-off of the thread-per-integral 1D kernels: an integral that has not met its
+    // tolerance after level `tail_level` is queued (its running sum parked in value[b]) and finished
+    // by k_adaptive1d_tail, one CTA per queued integral, in the same summation order
+    int tail_level;       // < 0: disabled
+    int* tail_count;
+    int* tail_idx;
 };
 
 template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP > 0 ? NP : 1], const Args<T>& a, long long b)
@@ -273,17 +284,33 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
         T s_new = num<T>::zero();
         const int n = 1 << level;
         const Node<T>* __restrict__ lv = nodes + (n - 2);
-        // two node pairs per trip (n = 2^level is even): 4 independent evaluations in flight,
-        // accumulated in the reference's order
-#pragma unroll 1
-        for (int i = 0; i < n; i += 2) {
-            const Node<T> n0 = ldg_node(lv + i), n1 = ldg_node(lv + i + 1);
+        // PAIRS node pairs per trip (n = 2^level): 2*PAIRS independent evaluations in flight,
+        // accumulated in the reference's order.  Level 1 has only two pairs.
+        if (level == 1) {
+            const Node<T> n0 = ldg_node(lv), n1 = ldg_node(lv + 1);
             const T d0 = dx * n0.x, d1 = dx * n1.x;
             const T xs[4] = {d0 + x0, x0 - d0, d1 + x0, x0 - d1};
             T fs[4];
             eval1d_n<T, F, FAST, 4>(xs, p, fs);
             s_new = muladd<T, FAST>(n0.w, fs[0] + fs[1], s_new);
             s_new = muladd<T, FAST>(n1.w, fs[2] + fs[3], s_new);
+        } else {
+            constexpr int PAIRS = TPI_PAIRS;
+#pragma unroll 1
+            for (int i = 0; i < n; i += PAIRS) {
+                T xs[2 * PAIRS], ws[PAIRS], fs[2 * PAIRS];
+#pragma unroll
+                for (int k = 0; k < PAIRS; ++k) {
+                    const Node<T> nd = ldg_node(lv + i + k);
+                    const T d = dx * nd.x;
+                    xs[2 * k] = d + x0;
+                    xs[2 * k + 1] = x0 - d;
+                    ws[k] = nd.w;
+                }
+                eval1d_n<T, F, FAST, 2 * PAIRS>(xs, p, fs);
+#pragma unroll
+                for (int k = 0; k < PAIRS; ++k) s_new = muladd<T, FAST>(ws[k], fs[2 * k] + fs[2 * k + 1], s_new);
+            }
         }
         s_total = s_total + s_new;
         const T new_res = dx * h * s_total;
@@ -293,6 +320,11 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
         if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
             flags |= FLAG_CONVERGED;
             break;
+        }
+        if (level == a.tail_level && level < a.max_levels) {  // park and let a whole CTA finish it
+            a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
+            a.value[b] = s_total;
+            return;
         }
     }
     if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
@@ -352,9 +384,97 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
             flags |= FLAG_CONVERGED;
             break;
         }
+        if (level == a.tail_level && level < a.max_levels) {  // park and let a whole CTA finish it
+            a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
+            a.value[b] = s_total;
+            return;
+        }
     }
     if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+}
+
+// Deep levels of queued 1D integrals (see Args::tail_level): one CTA per integral.  The CTA
+// evaluates a tile of w_i*(f(x+)+f(x-)) terms in parallel into shared memory, then ONE thread adds
+// them in index order, so the result is bit-identical to the sequential reference loop
+// (adaptive.jl:55-60 / 763-770) while the integrand work is spread over 256 threads.
+template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bounds__(256) k_adaptive1d_tail(const Args<T> a)
+{
+    constexpr int TILE = 1024;
+    __shared__ T terms[TILE];
+    __shared__ int s_done;
+    const int tid = threadIdx.x;
+    const int count = *a.tail_count;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const long long b = a.tail_idx[q];
+        T p[F::NP > 0 ? F::NP : 1];
+        load_params<F::NP>(p, a, b);
+        const T half = num<T>::half(), one = num<T>::one();
+        T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+        bool neg = false;
+        int flags = 0;
+        if (a.options & OPT_QUAD_EDGE) {
+            quad_edge_axis(lo, hi, neg);
+            if (neg) flags |= FLAG_FLIPPED;
+        }
+        const T dx = half * (hi - lo), x0 = half * (hi + lo);
+        T h = a.tm * half;
+        for (int l = 0; l < a.tail_level; ++l) h = h * half;
+        T s_total = a.value[b];
+        T old_res = dx * h * s_total;
+        T err = num<T>::zero();
+        int level_used = a.tail_level;
+        for (int level = a.tail_level + 1; level <= a.max_levels; ++level) {
+            h = h * half;
+            const int n = 1 << level;
+            T s_new = num<T>::zero();
+            for (int t0 = 0; t0 < n; t0 += TILE) {
+                const int m = n - t0 < TILE ? n - t0 : TILE;
+                for (int i = tid; i < m; i += blockDim.x) {
+                    if constexpr (CMPL) {
+                        const NodeC<T> nd = a.nodes_c[(n - 2) + t0 + i];
+                        const T dxck = dx * nd.c, dx1p = dx * (one + nd.x), d = dx * nd.x;
+                        terms[i] = nd.w * (F::template eval<T, FAST>(d + x0, dxck, dx1p, p) + F::template eval<T, FAST>(x0 - d, dx1p, dxck, p));
+                    } else {
+                        const Node<T> nd = ldg_node(a.nodes + (n - 2) + t0 + i);
+                        const T d = dx * nd.x;
+                        terms[i] = nd.w * (F::template eval<T, FAST>(d + x0, p) + F::template eval<T, FAST>(x0 - d, p));
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int i = 0; i < m; ++i) s_new = s_new + terms[i];
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                s_total = s_total + s_new;
+                const T new_res = dx * h * s_total;
+                err = fm::abs(new_res - old_res);
+                level_used = level;
+                old_res = new_res;
+                const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+                if (conv) flags |= FLAG_CONVERGED;
+                s_done = conv ? 1 : 0;
+            }
+            __syncthreads();
+            if (s_done) break;
+        }
+        if (tid == 0) {
+            if (!(flags & FLAG_CONVERGED)) flags |= FLAG_MAX_LEVELS;
+            store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+        }
+        __syncthreads();
+    }
+    // the last CTA to leave re-arms the (persistent, per-stream) queue for the next launch
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *a.tail_count = 0;
+            *a.ticket = 0u;
+        }
+    }
 }
 
 // integrand functors of kind FTS_KIND_2D_CMPL specialise this to true

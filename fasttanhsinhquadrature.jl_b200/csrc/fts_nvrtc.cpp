@@ -84,6 +84,9 @@ void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
             const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") + ">";
             if (fixed) v.push_back({dt, KID_FIXED_TPI, fast, std::string("fts::") + fixed + targs});
             if (adapt) v.push_back({dt, KID_ADAPT_TPI, fast, std::string("fts::") + adapt + targs});
+            if (kind == FTS_KIND_1D || kind == FTS_KIND_1D_CMPL)
+                v.push_back({dt, KID_ADAPT_TAIL, fast, std::string("fts::k_adaptive1d_tail<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") +
+                                                           (kind == FTS_KIND_1D_CMPL ? ", true>" : ", false>")});
         }
         if (dt != FTS_DD64) {
             const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand>";

@@ -177,6 +177,36 @@ def test_fast_cta_1d_matches_exact_sum(gpu, oracle):
     assert v.levels[0] == 12 and not v.converged[0] and rel(v.value[0], ref.value) <= 3e-14
 
 
+def test_deep_level_tail_keeps_reference_order(gpu, oracle):
+    """integrals that are still unconverged after level 8 leave the thread-per-integral kernel and
+    are finished by k_adaptive1d_tail (one CTA each, terms evaluated in parallel, added in index
+    order): values and levels must still match the sequential oracle."""
+    cache = gpu.adaptive_cache_1D(np.float64, max_levels=16)
+    oc = oracle.cache1d("f64", 16)
+    # a batch mixing easy integrals with sharply peaked ones that need levels 9..13
+    p0 = np.concatenate([np.full(500, 25.0), 10.0 ** np.linspace(3, 8, 12), np.full(500, 4.0)])
+    r = gpu.quad(gpu.builtin("runge"), -1.0, 1.0, rtol=1e-10, max_levels=16, cache=cache, params=p0, order="reference", full_output=True)
+    ref = oracle.batch_adaptive1d("f64", F["F1_RUNGE"], p0, [-1.0], [1.0], 1e-10, 0.0, 16, oc)
+    assert r.levels.max() >= 11 and (r.levels > 8).sum() >= 8
+    assert np.array_equal(r.levels, ref["level"])
+    assert rel(r.value, ref["value"]).max() <= 1e-15          # division and sqrt are correctly rounded: same order -> same bits (+-1 ulp)
+    assert np.array_equal(r.converged, ref["converged"])
+    # a single deep oscillatory integral (level 12 = max_levels, not converged, warn path)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        v = gpu.adaptive_integrate_1D(np.float64, gpu.builtin("sin2"), -PI, PI, rtol=1e-6, atol=1e-8, max_levels=12, params=[1000.0],
+                                      cache=gpu.adaptive_cache_1D(np.float64, max_levels=12), order="reference", full_output=True)
+    ro = oracle.adaptive1d("f64", F["F1_SIN2"], [1000.0], -PI, PI, 1e-6, 1e-8, 12, oracle.cache1d("f64", 12))
+    assert v.levels[0] == 12 and not v.converged[0] and (v.flags[0] & gpu.FLAG_MAX_LEVELS)
+    assert rel(v.value[0], ro.value) <= 3e-14                   # sin(1000x): libm vs CUDA differ by 1 ulp, amplified (problems.py)
+    # complement + Float32 through the same path
+    c32 = gpu.adaptive_cache_1D(np.float32, max_levels=12)
+    r32 = gpu.quad(gpu.builtin("runge"), np.float32(-1), np.float32(1), rtol=1e-6, max_levels=12, cache=c32, params=np.array([25.0, 1e5], np.float32),
+                   order="reference", full_output=True)
+    ref32 = oracle.batch_adaptive1d("f32", F["F1_RUNGE"], np.array([25.0, 1e5], np.float32), [-1.0], [1.0], 1e-6, 0.0, 12, oracle.cache1d("f32", 12))
+    assert np.array_equal(r32.levels, ref32["level"]) and rel(r32.value, ref32["value"]).max() <= 1e-6
+
+
 # ------------------------------------------------------------------ fixed grids ---------------
 def test_fixed_grid_1d_batch(gpu, oracle):
     """config A: integrate1D[_avx] of exp on [0, b_k], N in {80, 256, 1024}"""

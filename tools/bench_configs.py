@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Supplementary measurements for the BASELINE.json configs other than the headline one
+(bench.py measures configs[1]).  Every number is end to end through the host-buffer C ABI
+(PCIe copies included), best of `reps` after warm-up, one JSON line per case.
+
+    python tools/bench_configs.py [--cases A,C,D,E] [--reps 10]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "fasttanhsinhquadrature.jl_b200"))
+
+import numpy as np  # noqa: E402
+
+import fts_b200 as fts  # noqa: E402
+from fts_b200.api import evals_for_level  # noqa: E402
+
+FP64_PEAK = None
+
+
+def best_of(fn, reps):
+    fn()
+    fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), out
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def case_a(reps):
+    """config A: integrate1D[_avx] of exp on [0, 1+k 2^-20], precomputed (x,w,h); flop/eval 32.5"""
+    n = 1 << 20
+    up = 1.0 + np.arange(n) * 2.0 ** -20
+    low = np.zeros(n)
+    f = fts.builtin("exp")
+    for N in (80, 256, 1024):
+        x, w, h = fts.tanhsinh(np.float64, N)
+        for order in ("reference", "fast"):
+            t, v = best_of(lambda: fts.integrate1D(f, low, up, x, w, h, order=order), reps)
+            evals = n * (2 * (N // 2) + 1)
+            err = float(np.max(np.abs(v - (np.exp(up) - 1)) / (np.exp(up) - 1)))
+            emit(case="A", api="integrate1D" + ("_avx" if order == "fast" else ""), N=N, batch=n, ms=t * 1e3, integrals_per_s=n / t,
+                 gevals_per_s=evals / t / 1e9, fp64_frac_nominal=evals / t * 32.5 / 1e12 / FP64_PEAK, max_rel_err_vs_exact=err)
+
+
+def case_c(reps):
+    """config C: 4096 boxes, 1/sqrt((b-x)(y-c)), tensor-complement adaptive 2D; flop/eval 14.5"""
+    rng = np.random.default_rng(0)
+    n = 4096
+    low = np.stack([-3 + 2 * rng.random(n), -3 + 2 * rng.random(n)], axis=1)
+    up = np.stack([1 + 2 * rng.random(n), 1 + 2 * rng.random(n)], axis=1)
+    exact = 4 * np.sqrt((up[:, 0] - low[:, 0]) * (up[:, 1] - low[:, 1]))
+    f = fts.builtin("c2_invsqrt_bmx_ymc")
+    for T, rtol, ml in ((np.float64, 1e-10, 8), (np.float32, 1e-5, 6)):
+        cache = fts.adaptive_cache_2D_cmpl(T, max_levels=ml)
+        lo, hi = low.astype(T), up.astype(T)
+        t, r = best_of(lambda: fts.quad_cmpl(f, lo, hi, rtol=rtol, max_levels=ml, cache=cache, order="fast", full_output=True), reps)
+        evals = int(evals_for_level(2, r.levels).sum())
+        emit(case="C", dtype=np.dtype(T).name, batch=n, rtol=rtol, max_levels=ml, ms=t * 1e3, integrals_per_s=n / t, gevals_per_s=evals / t / 1e9,
+             levels=np.bincount(r.levels).tolist(), converged=int(r.converged.sum()),
+             max_rel_err_vs_exact=float(np.max(np.abs(r.value - exact) / exact)),
+             fp64_frac_nominal=(evals / t * 14.5 / 1e12 / FP64_PEAK) if T == np.float64 else None)
+
+
+def case_d(reps):
+    """config D on ONE GPU: a single adaptive 3D integral of exp(x+y+z), forced depth; flop/eval 32.1"""
+    f = fts.builtin("exp_3d")
+    exact = (math.e - 1 / math.e) ** 3
+    for L in (5, 6, 7, 8):
+        cache = fts.adaptive_cache_3D(np.float64, max_levels=L)
+        t, r = best_of(lambda: fts.adaptive_integrate_3D_avx(np.float64, f, [-1.0] * 3, [1.0] * 3, rtol=0.0, atol=0.0, max_levels=L, warn=False,
+                                                             cache=cache, full_output=True), max(3, reps // 2))
+        evals = int(evals_for_level(3, r.levels).sum())
+        emit(case="D", integrand="exp(x+y+z)", max_levels=L, level_reached=int(r.levels[0]), evals=evals, ms=t * 1e3, gevals_per_s=evals / t / 1e9,
+             rel_err_vs_exact=float(abs(r.value[0] - exact) / exact), fp64_frac_nominal=evals / t * 32.1 / 1e12 / FP64_PEAK)
+    # a genuinely large single integral: log(1-x)log(1-y)log(1-z) (test/families_3d.jl:64) keeps refining to max_levels
+    g = fts.builtin("log_3d")
+    exact_log = (2 * math.log(2) - 2) ** 3
+    for L in (7, 8):
+        cache = fts.adaptive_cache_3D(np.float64, max_levels=L)
+        t, r = best_of(lambda: fts.adaptive_integrate_3D_avx(np.float64, g, [-1.0] * 3, [1.0] * 3, rtol=0.0, atol=0.0, max_levels=L, warn=False,
+                                                             cache=cache, full_output=True), 3)
+        evals = int(evals_for_level(3, r.levels).sum())
+        emit(case="D", integrand="log(1-x)log(1-y)log(1-z)", max_levels=L, level_reached=int(r.levels[0]), evals=evals, ms=t * 1e3,
+             gevals_per_s=evals / t / 1e9, rel_err_vs_exact=float(abs(r.value[0] - exact_log) / abs(exact_log)))
+
+
+def case_e(reps):
+    """config E: Double64 quad_cmpl, 65536 integrals, rtol 1e-28"""
+    import mpmath
+    mpmath.mp.dps = 40
+    rng = np.random.default_rng(0)
+    n = 65536
+    a = -3 * rng.random(n); b = 0.5 + 3.5 * rng.random(n); c = 0.5 + 1.5 * rng.random(n)
+    cache = fts.adaptive_cache_1D(fts.Double64, max_levels=16, complement=True)
+    A, B, Cc = fts.to_dd(a), fts.to_dd(b), fts.to_dd(c)
+    for name, params in (("c_invsqrt", Cc), ("c_log_bmx", None)):
+        f = fts.builtin(name)
+        t, r = best_of(lambda: fts.quad_cmpl(f, A, B, rtol="1e-28", max_levels=16, cache=cache, params=params, full_output=True), max(3, reps // 3))
+        evals = int(evals_for_level(1, r.levels).sum())
+        idx = [0, n // 2, n - 1]
+        got = fts.dd_to_mpf(r.value[idx])
+        if name == "c_invsqrt":
+            want = [mpmath.mpf(float(c[i])) * mpmath.pi for i in idx]
+        else:
+            want = [(mpmath.mpf(float(b[i])) - mpmath.mpf(float(a[i]))) * (mpmath.log(mpmath.mpf(float(b[i])) - mpmath.mpf(float(a[i]))) - 1) for i in idx]
+        err = max(float(abs(g - w_) / abs(w_)) for g, w_ in zip(got, want))
+        emit(case="E", family=name, batch=n, ms=t * 1e3, integrals_per_s=n / t, gevals_per_s=evals / t / 1e9, levels=np.bincount(r.levels).tolist(),
+             converged=int(r.converged.sum()), max_rel_err_vs_exact_sampled=err)
+
+
+def main():
+    global FP64_PEAK
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="A,C,D,E")
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    fts.init(0)
+    FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
+    emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
+    for c in args.cases.split(","):
+        {"A": case_a, "C": case_c, "D": case_d, "E": case_e}[c](args.reps)
+
+
+if __name__ == "__main__":
+    main()
