@@ -145,7 +145,15 @@ struct F2Poly2 {
 };
 struct F2Exp {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return fm::exp(x + y); }
+    template <class T, bool FAST, int N> static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = x[i] + y[i];
+        exp_n<N>(a, f);
+    }
 };
 struct F2X2pY2 {
     static constexpr int NP = 0;
@@ -193,7 +201,16 @@ struct F3Poly2 {
 };
 struct F3Exp {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return fm::exp(x + y + z); }
+    template <class T, bool FAST, int N>
+    static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = x[i] + y[i] + z[i];
+        exp_n<N>(a, f);
+    }
 };
 struct F3X2Y2Z2 {
     static constexpr int NP = 0;

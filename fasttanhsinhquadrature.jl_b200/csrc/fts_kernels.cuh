@@ -91,6 +91,27 @@ template <class T, class F, bool FAST, int N> __device__ __forceinline__ void ev
     }
 }
 
+template <class T, class F, bool FAST, int N>
+__device__ __forceinline__ void eval2d_n(const T (&x)[N], const T (&y)[N], const T* p, T (&f)[N])
+{
+    if constexpr (HasEvalN<F>::value) {
+        F::template evaln<T, FAST, N>(x, y, p, f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], y[i], p);
+    }
+}
+template <class T, class F, bool FAST, int N>
+__device__ __forceinline__ void eval3d_n(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T* p, T (&f)[N])
+{
+    if constexpr (HasEvalN<F>::value) {
+        F::template evaln<T, FAST, N>(x, y, z, p, f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], y[i], z[i], p);
+    }
+}
+
 template <class T> __device__ __forceinline__ Node<T> ldg_node(const Node<T>* p) { return *p; }
 template <> __device__ __forceinline__ Node<double> ldg_node<double>(const Node<double>* p)
 {

@@ -213,6 +213,11 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ T cell2(const 
         const T bx = s.bx[i], ax = s.ax[i], dyc = s.dyc[j], cy = s.cy[j];
         f = (F::template eval<T, true>(xp, yp, bx, ax, dyc, cy, p) + F::template eval<T, true>(xm, yp, ax, bx, dyc, cy, p)) +
             (F::template eval<T, true>(xp, ym, bx, ax, cy, dyc, p) + F::template eval<T, true>(xm, ym, ax, bx, cy, dyc, p));
+    } else if constexpr (HasEvalN<F>::value) {
+        const T xs[4] = {xp, xm, xp, xm}, ys[4] = {yp, yp, ym, ym};
+        T v[4];
+        eval2d_n<T, F, true, 4>(xs, ys, p, v);
+        f = (v[0] + v[1]) + (v[2] + v[3]);
     } else {
         f = (F::template eval<T, true>(xp, yp, p) + F::template eval<T, true>(xm, yp, p)) +
             (F::template eval<T, true>(xp, ym, p) + F::template eval<T, true>(xm, ym, p));
@@ -387,12 +392,23 @@ template <class T> __device__ __forceinline__ void sm3_stage(Sm3<T>& s, const T*
     }
 }
 
+// Families with an interleaved batch evaluator (exp) get their 8 / 12 / 6 reflections evaluated
+// side by side; every other functor keeps the direct expression (the compiler then shares
+// sub-expressions between reflections, e.g. 6 logs instead of 24 for log(1-x)log(1-y)log(1-z)).
 #define FTS_FE(X, Y, Z) F::template eval<T, true>(X, Y, Z, p)
 template <class T, class F> __device__ __forceinline__ T cell3(const Sm3<T>& s, const T* p, int i, int j, int k)
 {
     const T xp = s.xp[i], xm = s.xm[i], yp = s.yp[j], ym = s.ym[j], zp = s.zp[k], zm = s.zm[k];
-    const T f = ((FTS_FE(xp, yp, zp) + FTS_FE(xm, yp, zp)) + (FTS_FE(xp, ym, zp) + FTS_FE(xm, ym, zp))) +
-                ((FTS_FE(xp, yp, zm) + FTS_FE(xm, yp, zm)) + (FTS_FE(xp, ym, zm) + FTS_FE(xm, ym, zm)));
+    T f;
+    if constexpr (HasEvalN<F>::value) {
+        const T xs[8] = {xp, xm, xp, xm, xp, xm, xp, xm}, ys[8] = {yp, yp, ym, ym, yp, yp, ym, ym}, zs[8] = {zp, zp, zp, zp, zm, zm, zm, zm};
+        T v[8];
+        eval3d_n<T, F, true, 8>(xs, ys, zs, p, v);
+        f = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    } else {
+        f = ((FTS_FE(xp, yp, zp) + FTS_FE(xm, yp, zp)) + (FTS_FE(xp, ym, zp) + FTS_FE(xm, ym, zp))) +
+            ((FTS_FE(xp, yp, zm) + FTS_FE(xm, yp, zm)) + (FTS_FE(xp, ym, zm) + FTS_FE(xm, ym, zm)));
+    }
     return (s.w[i] * s.w[j] * s.w[k]) * f;
 }
 template <class T, class F> __device__ __forceinline__ T plane3(const Sm3<T>& s, const T* p, int i, int j)
@@ -400,9 +416,19 @@ template <class T, class F> __device__ __forceinline__ T plane3(const Sm3<T>& s,
     const T x0 = s.x0, y0 = s.y0, z0 = s.z0;
     const T xp = s.xp[i], xm = s.xm[i], ypi = s.yp[i], ymi = s.ym[i];
     const T ypj = s.yp[j], ymj = s.ym[j], zpj = s.zp[j], zmj = s.zm[j];
-    const T f = ((FTS_FE(xp, ypj, z0) + FTS_FE(xm, ypj, z0)) + (FTS_FE(xp, ymj, z0) + FTS_FE(xm, ymj, z0))) +
-                ((FTS_FE(xp, y0, zpj) + FTS_FE(xm, y0, zpj)) + (FTS_FE(xp, y0, zmj) + FTS_FE(xm, y0, zmj))) +
-                ((FTS_FE(x0, ypi, zpj) + FTS_FE(x0, ymi, zpj)) + (FTS_FE(x0, ypi, zmj) + FTS_FE(x0, ymi, zmj)));
+    T f;
+    if constexpr (HasEvalN<F>::value) {
+        const T xs[12] = {xp, xm, xp, xm, xp, xm, xp, xm, x0, x0, x0, x0};
+        const T ys[12] = {ypj, ypj, ymj, ymj, y0, y0, y0, y0, ypi, ymi, ypi, ymi};
+        const T zs[12] = {z0, z0, z0, z0, zpj, zpj, zmj, zmj, zpj, zpj, zmj, zmj};
+        T v[12];
+        eval3d_n<T, F, true, 12>(xs, ys, zs, p, v);
+        f = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) + ((v[8] + v[9]) + (v[10] + v[11]));
+    } else {
+        f = ((FTS_FE(xp, ypj, z0) + FTS_FE(xm, ypj, z0)) + (FTS_FE(xp, ymj, z0) + FTS_FE(xm, ymj, z0))) +
+            ((FTS_FE(xp, y0, zpj) + FTS_FE(xm, y0, zpj)) + (FTS_FE(xp, y0, zmj) + FTS_FE(xm, y0, zmj))) +
+            ((FTS_FE(x0, ypi, zpj) + FTS_FE(x0, ymi, zpj)) + (FTS_FE(x0, ypi, zmj) + FTS_FE(x0, ymi, zmj)));
+    }
     return (s.w[i] * s.w[j] * s.w0) * f;
 }
 template <class T, class F> __device__ __forceinline__ T axis3(const Sm3<T>& s, const T* p, int i)

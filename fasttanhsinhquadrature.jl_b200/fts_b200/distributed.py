@@ -67,21 +67,26 @@ def quad_sharded(f, low, up, *, params=None, gather: bool = True, group=None, **
     return np.concatenate([o[: b - a].cpu().numpy() for o, (a, b) in zip(out, sizes)])
 
 
-def run_sharded_levels(max_levels: int, rank: int, world: int, level_fn: Callable, step_fn: Callable, all_gather: Callable):
+def run_sharded_levels(max_levels: int, rank: int, world: int, level_fn: Callable, step_fn: Callable, all_gather: Callable,
+                       shard_from_level: int = 0):
     """The level loop shared by the GPU path and the CPU (gloo) tests.
 
     level_fn(level, rank, world) -> this rank's partial of the level, a [2] tensor (s, c)
     all_gather(partial)          -> [world, 2] tensor in rank order
     step_fn(level, partials)     -> updates the state (stop test), returns nothing
+    Levels below `shard_from_level` are too small to be worth an exchange (level 3 of a 3D
+    integral has 3.7k cells): every rank computes them whole (rank 0 of 1) and skips the gather,
+    which keeps all ranks bit-identical and saves one collective latency per such level.
     No host synchronisation happens here."""
     for level in range(max_levels + 1):
-        partial = level_fn(level, rank, world)
-        partials = all_gather(partial)
-        step_fn(level, partials)
+        if level < shard_from_level:
+            step_fn(level, level_fn(level, 0, 1).view(1, 2))
+        else:
+            step_fn(level, all_gather(level_fn(level, rank, world)))
 
 
 def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
-                               warn: bool = True):
+                               warn: bool = True, shard_from_level: Optional[int] = None):
     """One large adaptive 2D/3D integral over all ranks of `group` (NCCL).  Returns an
     AdaptiveResult with one element, identical on every rank."""
     import torch
@@ -120,10 +125,12 @@ def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: 
         return gathered
 
     def step_fn(level, parts):
-        api.sharded_step_dev(cache, low=lo.data_ptr(), up=hi.data_ptr(), rtol=rtol_T[0], atol=atol_T[0], level=level, nranks=world,
+        api.sharded_step_dev(cache, low=lo.data_ptr(), up=hi.data_ptr(), rtol=rtol_T[0], atol=atol_T[0], level=level, nranks=parts.shape[0],
                              partials=parts.data_ptr(), state=state.data_ptr(), stream=stream)
 
-    run_sharded_levels(max_levels, rank, world, level_fn, step_fn, all_gather)
+    if shard_from_level is None:
+        shard_from_level = 0 if world == 1 else (5 if dim == 3 else 8)
+    run_sharded_levels(max_levels, rank, world, level_fn, step_fn, all_gather, shard_from_level)
     s = state.cpu().numpy()  # the only host synchronisation
     conv = s[5] != 0
     flags = np.array([L.FLAG_CONVERGED if conv else (L.FLAG_MAX_LEVELS if max_levels > 0 else 0)], np.int32)

@@ -96,6 +96,36 @@ def case_d(reps):
              gevals_per_s=evals / t / 1e9, rel_err_vs_exact=float(abs(r.value[0] - exact_log) / abs(exact_log)))
 
 
+def case_dk(reps):
+    """config D, kernel only: one refinement level of ONE 3D integral (k_level_grid), CUDA events"""
+    import torch
+    from fts_b200 import api
+    dev = torch.device("cuda", 0)
+    lo = torch.tensor([-1.0] * 3, dtype=torch.float64, device=dev)
+    up = torch.tensor([1.0] * 3, dtype=torch.float64, device=dev)
+    partial = torch.zeros(2, dtype=torch.float64, device=dev)
+    cache = fts.adaptive_cache_3D(np.float64, max_levels=8)
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, flop in (("exp_3d", 32.1), ("x2y2z2", 6.0), ("log_3d", None)):
+        f = fts.builtin(name)
+        for level in (6, 7, 8):
+            n = 2 << level
+            evals = 7 * n ** 3 + 9 * n ** 2 + 3 * n
+            ts = []
+            for it in range(reps + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                api.sharded_level_dev(cache, f, low=lo.data_ptr(), up=up.data_ptr(), params=0, level=level, rank=0, nranks=1,
+                                      partial=partial.data_ptr(), state=None, stream=stream)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ms = min(ts)
+            emit(case="D-kernel", integrand=name, level=level, new_evals=evals, ms=ms, gevals_per_s=evals / ms / 1e6,
+                 fp64_frac_nominal=(evals / ms / 1e-3 * flop / 1e12 / FP64_PEAK) if flop else None)
+
+
 def case_e(reps):
     """config E: Double64 quad_cmpl, 65536 integrals, rtol 1e-28"""
     import mpmath
@@ -130,7 +160,7 @@ def main():
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
     emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
     for c in args.cases.split(","):
-        {"A": case_a, "C": case_c, "D": case_d, "E": case_e}[c](args.reps)
+        {"A": case_a, "C": case_c, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
 
 
 if __name__ == "__main__":
