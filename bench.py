@@ -285,7 +285,8 @@ def main():
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
     roofline = {"bound": "fp64_pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
-                "traffic": None,
+                "traffic": 8406528,  # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_adaptive1d_tpi_*_ncu_full.md): the 8 MiB of alpha; outputs stay in L2
+
                 "peak_source": "in-run register-resident DFMA chain microbenchmark (fts_measure_fma_peak); MEASURED_PEAKS.json has no FP64 figure",
                 "peak_theoretical": FP64_THEORETICAL_TFLOPS, "frac_of_theoretical": achieved_tflops / FP64_THEORETICAL_TFLOPS,
                 "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": evals_per_step, "kernel": "k_adaptive1d_tpi<double,F1Gauss,false>",
