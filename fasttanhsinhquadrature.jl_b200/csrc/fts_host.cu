@@ -929,6 +929,112 @@ extern "C" int fts_adaptive_sharded_level_dev(fts_cache c, fts_integrand f, cons
     return set_error(FTS_ERR_UNSUPPORTED, "sharded levels: f32/f64 only");
 }
 
+// ---- fused path: peer-memory mailboxes + ONE call that queues every level ------------------------
+extern "C" int fts_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out)
+{
+    if (!dev_ptr || !ipc_handle_out || bytes == 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_peer_alloc: bad arguments");
+    if (int rc = ensure_init()) return rc;
+    FTS_CUDA(cudaMalloc(dev_ptr, bytes));
+    FTS_CUDA(cudaMemset(*dev_ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    FTS_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &h, sizeof h);
+    return FTS_OK;
+}
+extern "C" int fts_peer_open(const void* ipc_handle, void** dev_ptr)
+{
+    if (!dev_ptr || !ipc_handle) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_peer_open: bad arguments");
+    if (int rc = ensure_init()) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    FTS_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FTS_OK;
+}
+extern "C" int fts_peer_close(void* dev_ptr)
+{
+    if (dev_ptr) FTS_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return FTS_OK;
+}
+extern "C" int fts_peer_free(void* dev_ptr)
+{
+    if (dev_ptr) FTS_CUDA(cudaFree(dev_ptr));
+    return FTS_OK;
+}
+extern "C" int fts_peer_mailbox_bytes(int nranks, size_t* bytes)
+{
+    if (nranks < 1 || nranks > FTS_MAX_RANKS || !bytes) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad nranks");
+    *bytes = (size_t)2 * 64 * nranks * 4 * sizeof(double);  // [epoch parity][level < 64][rank]{s, c, flag, pad}
+    return FTS_OK;
+}
+
+template <class T>
+static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up, const T* params, T rtol, T atol, int max_levels,
+                         int shard_from, int rank, int nranks, void* const* mailboxes, double epoch, T* state, int options, cudaStream_t s)
+{
+    const int dim = kind_dim(f->kind);
+    const bool cmpl = kind_cmpl(f->kind);
+    const void* fn = integrand_kernel(f, c->dtype, KID_LEVEL_GRID, 1);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no whole-grid level kernel for this integrand/dtype");
+    const size_t nblk = (size_t)g_prop.multiProcessorCount * 4;
+    T* scratch = nullptr;
+    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2 + 2) * sizeof(T), s));
+    T* partial = scratch + 2 * nblk;
+    unsigned int* ticket = (unsigned int*)(partial + 2);
+    FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    const T tm = load_elem<T>(c->tm);
+    const int parity = ((long long)epoch) & 1;
+    for (int level = 0; level <= max_levels; ++level) {
+        const bool shard = mailboxes != nullptr && level >= shard_from;  // nranks == 1 with a mailbox exercises the flag protocol on one GPU
+        fts::Args<T> a;
+        memset(&a, 0, sizeof a);
+        fill_cache_args(a, c);
+        a.low = low; a.up = up; a.params = params; a.bstride = dim; a.pstride = 0; a.batch = 1;
+        a.level = level; a.rank = shard ? rank : 0; a.nranks = shard ? nranks : 1;
+        a.block_partials = scratch; a.ticket = ticket; a.partial_out = partial; a.state = level ? state : nullptr;
+        if (shard) {
+            for (int r = 0; r < nranks; ++r) a.peer_mail[r] = (double*)mailboxes[r];
+            a.mail_slot = parity * 64 + level;
+            a.epoch = epoch;
+        }
+        if (int rc = launch_raw(fn, grid_level_blocks(dim, level, a.nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s)) return rc;
+        if (shard) {
+            if (dim == 3) fts::k_sharded_step_fused<T, 3><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options);
+            else fts::k_sharded_step_fused<T, 2><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options);
+            g_launches.fetch_add(1);
+        } else {
+            if (dim == 3) launch_step<T, 3>(low, up, tm, rtol, atol, level, 1, partial, state, s, options);
+            else launch_step<T, 2>(low, up, tm, rtol, atol, level, 1, partial, state, s, options);
+        }
+    }
+    FTS_CUDA(cudaGetLastError());
+    FTS_CUDA(cudaFreeAsync(scratch, s));
+    return FTS_OK;
+}
+
+extern "C" int fts_adaptive_sharded_fused_dev(fts_cache c, fts_integrand f, const void* low, const void* up, const void* params,
+                                              const void* rtol, const void* atol, int max_levels, int shard_from_level, int rank, int nranks,
+                                              void* const* mailboxes, uint64_t epoch, void* state_dev, void* stream)
+{
+    if (!c || !f || !low || !up || !rtol || !atol || !state_dev) return set_error(FTS_ERR_INVALID_ARGUMENT, "sharded fused: null argument");
+    if (int rc = check_cache_match(c, f)) return rc;
+    if (kind_dim(f->kind) < 2) return set_error(FTS_ERR_UNSUPPORTED, "outer-axis sharding exists for 2D/3D integrals");
+    if (max_levels < 0 || max_levels > c->max_levels || max_levels >= 64)
+        return set_error(FTS_ERR_INVALID_ARGUMENT, "provided adaptive cache supports " + std::to_string(c->max_levels) + " levels, but `max_levels=" + std::to_string(max_levels) + "` was requested.");
+    if (nranks < 1 || nranks > FTS_MAX_RANKS || rank < 0 || rank >= nranks) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad rank/nranks");
+    if (nranks > 1 && (!mailboxes || epoch == 0)) return set_error(FTS_ERR_INVALID_ARGUMENT, "sharded fused: mailboxes and a non-zero epoch are required");
+    if (f->nparams > 0 && !params) return set_error(FTS_ERR_INVALID_ARGUMENT, "integrand needs parameters");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->dtype == FTS_F64)
+        return sharded_fused<double>(c, f, (const double*)low, (const double*)up, (const double*)params, load_elem<double>(rtol), load_elem<double>(atol),
+                                     max_levels, shard_from_level, rank, nranks, mailboxes, (double)epoch, (double*)state_dev, 0, s);
+    if (c->dtype == FTS_F32)
+        return sharded_fused<float>(c, f, (const float*)low, (const float*)up, (const float*)params, load_elem<float>(rtol), load_elem<float>(atol),
+                                    max_levels, shard_from_level, rank, nranks, mailboxes, (double)epoch, (float*)state_dev, 0, s);
+    return set_error(FTS_ERR_UNSUPPORTED, "sharded fused: f32/f64 only");
+}
+
 extern "C" int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up, const void* rtol, const void* atol, int level,
                                              int nranks, const void* partials_dev, void* state_dev, void* stream)
 {

@@ -20,6 +20,9 @@ namespace fts {
 enum : int { OPT_QUAD_EDGE = 1 };
 enum : int { FLAG_CONVERGED = 1, FLAG_MAX_LEVELS = 2, FLAG_ZERO_WIDTH = 4, FLAG_FLIPPED = 8 };
 
+#ifndef FTS_MAX_RANKS
+#define FTS_MAX_RANKS 16
+#endif
 #ifndef FTS_TPI_PAIRS
 #define FTS_TPI_PAIRS 4
 #endif
@@ -66,6 +69,11 @@ template <class T> struct Args {
     int tail_level;       // < 0: disabled
     int* tail_count;
     int* tail_idx;
+    // fused exchange over NVLink peer memory (k_level_grid epilogue): the last CTA stores this
+    // rank's (s, c) and then the epoch flag straight into every rank's mailbox
+    double* peer_mail[FTS_MAX_RANKS];  // mailbox of rank r mapped into this process (own one included); null: no exchange
+    int mail_slot;                     // index of this launch's slot row: (epoch&1)*levels + level
+    double epoch;                      // flag value of this call
 };
 
 template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP > 0 ? NP : 1], const Args<T>& a, long long b)

@@ -664,6 +664,97 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
         a.partial_out[1] = tot.c;
         *a.ticket = 0u;
     }
+    // fused all-gather: one lane per destination rank writes {s, c} into that rank's mailbox over
+    // NVLink (or locally for r == rank), fences system-wide, then raises the epoch flag
+    if (a.peer_mail[0] != nullptr && tid < a.nranks) {
+        const double s_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.s, 0));
+        const double c_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.c, 0));
+        volatile double* slot = a.peer_mail[tid] + ((size_t)a.mail_slot * a.nranks + a.rank) * 4;
+        slot[0] = s_;
+        slot[1] = c_;
+        __threadfence_system();
+        slot[2] = a.epoch;
+    }
+}
+
+// Stop test of the fused path: lane r of one warp waits for rank r's flag in OUR mailbox (peers
+// write it through NVLink), then thread 0 does the arithmetic of k_sharded_step.  A rank that never
+// arrives trips a 2 s timeout -> state[5] = 3 and every later launch of the call exits.
+template <class T, int D> __global__ void k_sharded_step_fused(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
+                                                               const double* mail, int mail_slot, double epoch, T* state, int options)
+{
+    __shared__ int s_ok;
+    if (level > 0 && state[5] != num<T>::zero()) return;
+    const int lane = threadIdx.x;
+    if (lane == 0) s_ok = 1;
+    __syncwarp();
+    if (lane < nranks) {
+        const volatile double* slot = mail + ((size_t)mail_slot * nranks + lane) * 4;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (slot[2] != epoch) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ULL) {
+                s_ok = 0;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (lane != 0) return;
+    if (!s_ok) {
+        state[5] = num<T>::from_double(3.0);
+        return;
+    }
+    if (level == 0 && (options & OPT_QUAD_EDGE)) {
+        bool zero = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) zero = zero || (low[d] == up[d]);
+        if (zero) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) state[i] = num<T>::zero();
+            state[5] = num<T>::from_double(2.0);
+            return;
+        }
+    }
+    const T half = num<T>::half();
+    Comp<T> tot;
+    if (level > 0) {
+        tot.s = state[0];
+        tot.c = state[1];
+    }
+    for (int r = 0; r < nranks; ++r) {
+        const volatile double* slot = mail + ((size_t)mail_slot * nranks + r) * 4;
+        Comp<T> o;
+        o.s = num<T>::from_double(slot[0]);
+        o.c = num<T>::from_double(slot[1]);
+        tot.merge(o);
+    }
+    T scale = num<T>::one();
+#pragma unroll
+    for (int d = 0; d < D; ++d) scale = scale * (half * (up[d] - low[d]));
+    const T h = level == 0 ? tm * half : state[7] * half;
+    T hD = h;
+#pragma unroll
+    for (int d = 1; d < D; ++d) hD = hD * h;
+    const T res = scale * hD * tot.value();
+    state[0] = tot.s;
+    state[1] = tot.c;
+    state[7] = h;
+    state[6] = num<T>::from_double((double)level);
+    if (level == 0) {
+        state[2] = res;
+        state[3] = res;
+        state[4] = num<T>::zero();
+        state[5] = num<T>::zero();
+    } else {
+        const T err = fm::abs(res - state[2]);
+        state[2] = res;
+        state[3] = res;
+        state[4] = err;
+        if (err <= fm::err_target(res, rtol, atol)) state[5] = num<T>::one();
+    }
 }
 
 // Stop test after the partials of all ranks are known (adaptive.jl:693-700): one thread,

@@ -80,6 +80,12 @@ _SIGS = {
     "fts_adaptive_batch_dev": (ci, [vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, i64, vp, vp, vp, vp, vp]),
     "fts_adaptive_sharded_level_dev": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]),
     "fts_adaptive_sharded_step_dev": (ci, [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp]),
+    "fts_peer_mailbox_bytes": (ci, [ci, C.POINTER(cs_)]),
+    "fts_peer_alloc": (ci, [cs_, C.POINTER(vp), vp]),
+    "fts_peer_open": (ci, [vp, C.POINTER(vp)]),
+    "fts_peer_close": (ci, [vp]),
+    "fts_peer_free": (ci, [vp]),
+    "fts_adaptive_sharded_fused_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp), C.c_uint64, vp, vp]),
     "fts_integrand_cubin_size": (ci, [vp, C.POINTER(cs_), C.POINTER(ci)]),
     "fts_measure_fma_peak": (ci, [ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fts_launch_count": (i64, [ci]),

@@ -85,10 +85,61 @@ def run_sharded_levels(max_levels: int, rank: int, world: int, level_fn: Callabl
             step_fn(level, all_gather(level_fn(level, rank, world)))
 
 
+class PeerMailboxes:
+    """NVLink peer-memory mailboxes of the fused exchange (fts_adaptive_sharded_fused_dev): every
+    rank owns one small device buffer; its cudaIpc handle is all-gathered once and every peer maps
+    it, after which the level kernels store their partials straight into each other's memory."""
+
+    _cache: dict = {}
+
+    def __init__(self, group=None):
+        import ctypes as C
+        import torch
+        dist = _dist()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        nbytes = C.c_size_t()
+        L.check(L.lib.fts_peer_mailbox_bytes(self.world, C.byref(nbytes)))
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        L.check(L.lib.fts_peer_alloc(nbytes.value, C.byref(own), handle))
+        self.own = own
+        self.ptrs = (C.c_void_p * self.world)()
+        self.ptrs[self.rank] = own.value
+        self.opened = []
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+            allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().numpy().reshape(self.world, 64)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                hb = (C.c_ubyte * 64)(*allh[r].tolist())
+                ptr = C.c_void_p()
+                L.check(L.lib.fts_peer_open(hb, C.byref(ptr)))
+                self.ptrs[r] = ptr.value
+                self.opened.append(ptr)
+            dist.barrier(group=group)
+        self.epoch = 0
+
+    @classmethod
+    def get(cls, group=None) -> "PeerMailboxes":
+        key = id(group)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group)
+        return cls._cache[key]
+
+
 def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
-                               warn: bool = True, shard_from_level: Optional[int] = None):
-    """One large adaptive 2D/3D integral over all ranks of `group` (NCCL).  Returns an
-    AdaptiveResult with one element, identical on every rank."""
+                               warn: bool = True, shard_from_level: Optional[int] = None, exchange: str = "peer"):
+    """One large adaptive 2D/3D integral over all ranks of `group`.  Returns an AdaptiveResult
+    with one element, identical on every rank.
+
+    exchange="peer": the fused path — level kernels store their partials into every rank's
+    mailbox over NVLink peer memory, the stop test waits on the device; ONE C call queues all
+    levels.  exchange="nccl": level kernel -> NCCL all-gather -> stop-test kernel per level."""
     import torch
     dist = _dist()
     dt = api._dt(T)
@@ -129,9 +180,20 @@ def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: 
                              partials=parts.data_ptr(), state=state.data_ptr(), stream=stream)
 
     if shard_from_level is None:
-        shard_from_level = 0 if world == 1 else (5 if dim == 3 else 8)
-    run_sharded_levels(max_levels, rank, world, level_fn, step_fn, all_gather, shard_from_level)
+        shard_from_level = (max_levels + 1 if exchange == "peer" else 0) if world == 1 else (5 if dim == 3 else 8)
+    if exchange == "peer":
+        import ctypes as C
+        mb = PeerMailboxes.get(group)
+        mb.epoch += 1
+        L.check(L.lib.fts_adaptive_sharded_fused_dev(
+            cache.handle, f._h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(p.data_ptr()) if p is not None else None,
+            api._ptr(rtol_T), api._ptr(atol_T), max_levels, shard_from_level, rank, world, mb.ptrs, C.c_uint64(mb.epoch),
+            C.c_void_p(state.data_ptr()), C.c_void_p(stream)))
+    else:
+        run_sharded_levels(max_levels, rank, world, level_fn, step_fn, all_gather, shard_from_level)
     s = state.cpu().numpy()  # the only host synchronisation
+    if s[5] == 3:
+        raise api.FtsError(L.ERR_CUDA, "sharded integral: a rank did not deliver its level partial within 2 s (peer exchange timed out)")
     conv = s[5] != 0
     flags = np.array([L.FLAG_CONVERGED if conv else (L.FLAG_MAX_LEVELS if max_levels > 0 else 0)], np.int32)
     res = api.AdaptiveResult(np.array([s[3]], dt), np.array([s[4]], dt), np.array([int(s[6])], np.int32), flags)

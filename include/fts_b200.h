@@ -267,6 +267,26 @@ int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up,
                                   const void* rtol, const void* atol, int level, int nranks,
                                   const void* partials_dev, void* state_dev, void* stream);
 
+/* Fused variant ("one kernel does the compute and the exchange"): ONE call queues every level of
+ * the integral.  The epilogue of each level kernel stores this rank's (s, c) and then an epoch
+ * flag straight into every rank's MAILBOX over NVLink peer memory (cudaIpc-mapped device
+ * buffers), and the device-side stop test of every rank waits for the flags in its own mailbox
+ * (2 s timeout -> state done = 3).  No NCCL call and no host involvement between levels; levels
+ * below `shard_from_level` are too small to shard and are computed whole on every rank.
+ * mailboxes[r] = rank r's mailbox mapped into this process (fts_peer_alloc on the owner,
+ * fts_peer_open elsewhere; size fts_peer_mailbox_bytes); epoch = 1, 2, 3 ... incremented by the
+ * caller once per call, identical on all ranks. */
+int fts_peer_mailbox_bytes(int nranks, size_t* bytes);
+int fts_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out /* 64 bytes */);
+int fts_peer_open(const void* ipc_handle /* 64 bytes */, void** dev_ptr);
+int fts_peer_close(void* dev_ptr);
+int fts_peer_free(void* dev_ptr);
+int fts_adaptive_sharded_fused_dev(fts_cache c, fts_integrand f, const void* low, const void* up,
+                                   const void* params, const void* rtol, const void* atol,
+                                   int max_levels, int shard_from_level, int rank, int nranks,
+                                   void* const* mailboxes, uint64_t epoch, void* state_dev,
+                                   void* stream);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Register-resident DFMA (dtype FTS_F64) / FFMA (FTS_F32) chain microbenchmark: the measured
  * pipe peak used as the roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */

@@ -421,6 +421,28 @@ def test_sharded_levels_emulated_ranks(gpu, oracle):
     assert s1[5] == 1 and int(s1[6]) == ref.level and rel(s1[3], s[3]) <= 2e-16
 
 
+def test_fused_sharded_path_single_rank(gpu, oracle):
+    """fts_adaptive_sharded_fused_dev on one rank: the whole level loop queued by ONE call, the
+    mailbox/flag protocol exercised through the rank's own mailbox (forced with shard_from_level=0
+    and a 1-rank "world" is not exchanged, so drive the kernels through a 1-entry mailbox table)."""
+    from fts_b200 import distributed as fd
+    f = gpu.builtin("exp_3d")
+    cache = gpu.adaptive_cache_3D(np.float64, max_levels=5)
+    lo, up = [-2.0, -1.0, 0.0], [3.0, 2.0, 4.0]
+    ref = oracle.adaptive_nd("f64x", 3, F["F3_EXP"], None, lo, up, 1e-9, 0.0, 5, oracle.cache_tensor("f64", 3, 5))
+    for exchange, sfl in (("peer", None), ("peer", 0), ("peer", 3), ("nccl", None)):
+        r = fd.adaptive_integrate_sharded(np.float64, f, lo, up, rtol=1e-9, max_levels=5, cache=cache, exchange=exchange, shard_from_level=sfl)
+        assert r.levels[0] == ref.level and r.converged[0] and rel(r.value[0], ref.value) <= RTOL64, (exchange, sfl)
+    # repeated calls advance the epoch and alternate the mailbox parity
+    for _ in range(3):
+        r = fd.adaptive_integrate_sharded(np.float64, f, lo, up, rtol=1e-9, max_levels=5, cache=cache, shard_from_level=0)
+        assert r.levels[0] == ref.level and rel(r.value[0], ref.value) <= RTOL64
+    r2 = fd.adaptive_integrate_sharded(np.float64, gpu.builtin("exp_2d"), [-1.0, -1.0], [1.0, 1.0], rtol=1e-12, max_levels=8,
+                                       cache=gpu.adaptive_cache_2D(np.float64, max_levels=8))
+    ref2 = oracle.adaptive_nd("f64x", 2, F["F2_EXP"], None, [-1, -1], [1, 1], 1e-12, 0.0, 8, oracle.cache_tensor("f64", 2, 8))
+    assert r2.levels[0] == ref2.level and rel(r2.value[0], ref2.value) <= RTOL64
+
+
 # ------------------------------------------------------------------ semantics -----------------
 def test_quad_semantics_and_warnings(gpu):
     p7 = gpu.builtin("poly7")

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--integrand", default="log_3d")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--rtol", type=float, default=0.0)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -51,7 +52,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = fd.adaptive_integrate_sharded(np.float64, f, low, up, rtol=args.rtol, atol=0.0, max_levels=args.levels, cache=cache, warn=False)
+        r = fd.adaptive_integrate_sharded(np.float64, f, low, up, rtol=args.rtol, atol=0.0, max_levels=args.levels, cache=cache, warn=False, exchange=args.exchange)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -68,7 +69,7 @@ def main():
     if rank == 0:
         evals = int(evals_for_level(3, r.levels)[0])
         ms = min(times)
-        print(json.dumps({"case": "D-sharded", "integrand": args.integrand, "n_gpus": world, "max_levels": args.levels, "level_reached": int(r.levels[0]),
+        print(json.dumps({"case": "D-sharded", "exchange": args.exchange, "integrand": args.integrand, "n_gpus": world, "max_levels": args.levels, "level_reached": int(r.levels[0]),
                           "value": float(r.value[0]), "rel_err_vs_exact": abs(float(r.value[0]) - exact) / abs(exact),
                           "identical_on_all_ranks": bool(all(float(v.item()) == float(r.value[0]) for v in allv)), "evals": evals, "ms": ms,
                           "ms_median": sorted(times)[len(times) // 2], "gevals_per_s": evals / ms / 1e6}))
