@@ -88,7 +88,7 @@ struct F1InvSqrt1mx2 {  // 1/sqrt(1-x^2)   benchmarks.jl:36
     static constexpr int NP = 0;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*)
     {
-        return num<T>::one() / fm::sqrt(muladd<T, FAST>(-x, x, num<T>::one()));
+        return fm::inv_sqrt<FAST>(muladd<T, FAST>(-x, x, num<T>::one()));
     }
 };
 struct F1Sin2 {  // sin(1000x)^2   benchmarks.jl:37
@@ -164,12 +164,12 @@ struct F2InvSqrt {
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*)
     {
         const T one = num<T>::one();
-        return one / fm::sqrt(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one));
+        return fm::inv_sqrt<FAST>(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one));
     }
 };
 struct F2InvSqrtAbs {
     static constexpr int NP = 0;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return num<T>::one() / fm::sqrt(fm::abs(x * y)); }
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return fm::inv_sqrt<FAST>(fm::abs(x * y)); }
 };
 
 // ---------------------------------------------------------------- 2D complement -------------
@@ -177,14 +177,14 @@ struct C2InvSqrtBmxYmc {  // 1/sqrt((b-x)(y-c))   BASELINE config C
     static constexpr int NP = 0;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T bmx, T, T, T ymc, const T*)
     {
-        return num<T>::one() / fm::sqrt(bmx * ymc);
+        return fm::inv_sqrt<FAST>(bmx * ymc);
     }
 };
 struct C2InvSqrtAll {
     static constexpr int NP = 0;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T bmx, T xma, T dmy, T ymc, const T*)
     {
-        return num<T>::one() / fm::sqrt(bmx * xma * dmy * ymc);
+        return fm::inv_sqrt<FAST>(bmx * xma * dmy * ymc);
     }
 };
 
@@ -221,7 +221,7 @@ struct F3InvSqrt {
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*)
     {
         const T one = num<T>::one();
-        return one / fm::sqrt(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one) * muladd<T, FAST>(-z, z, one));
+        return fm::inv_sqrt<FAST>(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one) * muladd<T, FAST>(-z, z, one));
     }
 };
 struct F3Rat {
@@ -243,7 +243,7 @@ struct F3Log {
 };
 struct F3InvSqrtAbs {
     static constexpr int NP = 0;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return num<T>::one() / fm::sqrt(fm::abs(x * y * z)); }
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return fm::inv_sqrt<FAST>(fm::abs(x * y * z)); }
 };
 
 }  // namespace fts

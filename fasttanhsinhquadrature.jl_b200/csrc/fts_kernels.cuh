@@ -173,7 +173,24 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
     const T dx = half * (hi - lo), x0 = half * (hi + lo);  // core.jl:27-30
     T s = num<T>::half_pi() * F::template eval<T, FAST>(x0, p);
     const int n = a.n;
-    for (int i = 0; i < n; ++i) {
+    constexpr int PAIRS = TPI_PAIRS;
+    int i = 0;
+#pragma unroll 1
+    for (; i + PAIRS <= n; i += PAIRS) {  // PAIRS node pairs = 2*PAIRS independent evaluations per trip, summed in order
+        T xs[2 * PAIRS], ws[PAIRS], fs[2 * PAIRS];
+#pragma unroll
+        for (int k = 0; k < PAIRS; ++k) {
+            const Node<T> nd = ldg_node(a.grid + i + k);
+            const T d = dx * nd.x;
+            xs[2 * k] = x0 - d;      // f(xm) + f(xp) in this order (integrate1D.jl:97-99)
+            xs[2 * k + 1] = x0 + d;
+            ws[k] = nd.w;
+        }
+        eval1d_n<T, F, FAST, 2 * PAIRS>(xs, p, fs);
+#pragma unroll
+        for (int k = 0; k < PAIRS; ++k) s = muladd<T, FAST>(ws[k], fs[2 * k] + fs[2 * k + 1], s);
+    }
+    for (; i < n; ++i) {
         const Node<T> nd = ldg_node(a.grid + i);
         const T d = dx * nd.x;
         const T xp = x0 + d, xm = x0 - d;

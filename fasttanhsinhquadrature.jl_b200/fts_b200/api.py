@@ -135,6 +135,14 @@ def adaptive_batch_dev(cache, f, *, low, up, bounds_stride, params, params_strid
                                          C.c_void_p(flags) if flags else None, C.c_void_p(stream) if stream else None))
 
 
+def integrate_batch_dev(x, w, h, f, *, low, up, bounds_stride, params, params_stride, batch, value, stream=None, order="reference") -> None:
+    """Asynchronous fixed-grid launch on DEVICE buffers (raw pointers as ints): fts_integrate_batch_dev."""
+    handle = _tables.get(x, w, h)
+    L.check(L.lib.fts_integrate_batch_dev(handle, f._h, _order(order), C.c_void_p(low), C.c_void_p(up), bounds_stride,
+                                          C.c_void_p(params) if params else None, params_stride, batch, C.c_void_p(value),
+                                          C.c_void_p(stream) if stream else None))
+
+
 def adaptive_batch_host(cache, f, *, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, value, err=None,
                         levels=None, flags=None, order="reference", options=0) -> None:
     """Synchronous call on HOST buffers (raw pointers; pinned memory makes the copies DMA):

@@ -54,6 +54,38 @@ def case_a(reps):
                  gevals_per_s=evals / t / 1e9, fp64_frac_nominal=evals / t * 32.5 / 1e12 / FP64_PEAK, max_rel_err_vs_exact=err)
 
 
+def case_adev(reps):
+    """config A with inputs resident in HBM: kernel-only time (CUDA events), reference and FMA order"""
+    import torch
+    from fts_b200 import api
+    dev = torch.device("cuda", 0)
+    n = 1 << 20
+    up_np = 1.0 + np.arange(n) * 2.0 ** -20
+    up = torch.from_numpy(up_np).to(dev)
+    low = torch.zeros(n, dtype=torch.float64, device=dev)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    f = fts.builtin("exp")
+    stream = torch.cuda.current_stream().cuda_stream
+    for N in (80, 256, 1024):
+        x, w, h = fts.tanhsinh(np.float64, N)
+        for order in ("reference", "fast"):
+            ts = []
+            for it in range(reps + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                api.integrate_batch_dev(x, w, h, f, low=low.data_ptr(), up=up.data_ptr(), bounds_stride=1, params=0, params_stride=0, batch=n,
+                                        value=out.data_ptr(), stream=stream, order=order)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ms = min(ts)
+            evals = n * (2 * (N // 2) + 1)
+            err = float(np.max(np.abs(out.cpu().numpy() - (np.exp(up_np) - 1)) / (np.exp(up_np) - 1)))
+            emit(case="A-device", api="integrate1D" + ("_avx" if order == "fast" else ""), N=N, batch=n, ms=ms, integrals_per_s=n / ms * 1e3,
+                 gevals_per_s=evals / ms / 1e6, fp64_frac_nominal=evals / ms * 1e3 * 32.5 / 1e12 / FP64_PEAK, max_rel_err_vs_exact=err)
+
+
 def case_c(reps):
     """config C: 4096 boxes, 1/sqrt((b-x)(y-c)), tensor-complement adaptive 2D; flop/eval 14.5"""
     rng = np.random.default_rng(0)
@@ -160,7 +192,7 @@ def main():
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
     emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
     for c in args.cases.split(","):
-        {"A": case_a, "C": case_c, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
+        {"A": case_a, "Adev": case_adev, "C": case_c, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
 
 
 if __name__ == "__main__":
