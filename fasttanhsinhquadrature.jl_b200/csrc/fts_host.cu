@@ -3,6 +3,7 @@
 // requires an sm_100 device and fails with FTS_ERR_NO_DEVICE / FTS_ERR_CUDA otherwise.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -858,7 +859,8 @@ extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int o
 
     const int64_t kMinChunk = 1 << 16;
     int nch = 1;
-    if (dim == 1 || batch >= 8 * kMinChunk) nch = (int)(batch / kMinChunk < 8 ? batch / kMinChunk : 8);
+    static const int kMaxChunks = [] { const char* e = getenv("FTS_B200_CHUNKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 32 ? 32 : v); }();
+    if (dim == 1 || batch >= 8 * kMinChunk) nch = (int)(batch / kMinChunk < kMaxChunks ? batch / kMinChunk : kMaxChunks);
     if (nch < 1) nch = 1;
     // broadcast operands go first on the main stream; the pipeline streams wait for them
     if (!bounds_stride) {
