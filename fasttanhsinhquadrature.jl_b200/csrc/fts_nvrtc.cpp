@@ -24,6 +24,7 @@ extern const char fts_src_dd[];       // fts_dd.cuh
 extern const char fts_src_math[];     // fts_math.cuh      (generated: build/fts_embedded_src.cpp)
 extern const char fts_src_kernels[];  // fts_kernels.cuh
 extern const char fts_src_cta[];      // fts_kernels_cta.cuh
+extern const char fts_src_exp_table[];  // fts_exp_table.inc
 
 namespace {
 
@@ -126,10 +127,10 @@ int compile(const std::string& body, int kind, int nparams, Program* m, bool wan
     src += "\n    }\n};\n";
     if (kind == FTS_KIND_2D_CMPL) src += "namespace fts { template <> struct is_cmpl2d<FtsUserIntegrand> { static constexpr bool value = true; }; }\n";
 
-    const char* hdr_src[] = {fts_src_dd, fts_src_math, fts_src_kernels, fts_src_cta};
-    const char* hdr_name[] = {"fts_dd.cuh", "fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh"};
+    const char* hdr_src[] = {fts_src_dd, fts_src_math, fts_src_kernels, fts_src_cta, fts_src_exp_table};
+    const char* hdr_name[] = {"fts_dd.cuh", "fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh", "fts_exp_table.inc"};
     nvrtcProgram prog = nullptr;
-    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 4, hdr_src, hdr_name);
+    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 5, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) return nvrtc_fail(r, "nvrtcCreateProgram", nullptr, log, loglen);
     add_specs(m->specs, kind, want_dd);
     for (auto& s : m->specs) {
