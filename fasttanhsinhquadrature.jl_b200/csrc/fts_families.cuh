@@ -55,19 +55,21 @@ struct F1Exp {
     static constexpr int NP = 0;
     static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::exp(x); }
-    template <class T, bool FAST, int N> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N]) { exp_n<N>(x, f); }
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N]) { exp_n<N, MODE>(x, f); }
+    template <class T> static __device__ __forceinline__ T exp_arg_bound(T reach, const T*) { return reach; }  // max |x| over the interval
 };
 struct F1Gauss {  // exp(-α*x^2)   README.md:102
     static constexpr int NP = 1;
     static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p) { return fm::exp(-p[0] * (x * x)); }
-    template <class T, bool FAST, int N> static __device__ __forceinline__ void evaln(const T (&x)[N], const T* p, T (&f)[N])
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T* p, T (&f)[N])
     {
         T a[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) a[i] = -p[0] * (x[i] * x[i]);
-        exp_n<N>(a, f);
+        exp_n<N, MODE>(a, f);
     }
+    template <class T> static __device__ __forceinline__ T exp_arg_bound(T reach, const T* p) { return fm::abs(p[0]) * (reach * reach); }
 };
 struct F1Runge {  // 1/(1+25x^2)   benchmarks.jl:34
     static constexpr int NP = 1;
@@ -147,13 +149,14 @@ struct F2Exp {
     static constexpr int NP = 0;
     static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return fm::exp(x + y); }
-    template <class T, bool FAST, int N> static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T*, T (&f)[N])
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T*, T (&f)[N])
     {
         T a[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) a[i] = x[i] + y[i];
-        exp_n<N>(a, f);
+        exp_n<N, MODE>(a, f);
     }
+    template <class T> static __device__ __forceinline__ T exp_arg_bound(T reach, const T*) { return reach; }  // reach = sum over axes of |c|+|d|
 };
 struct F2X2pY2 {
     static constexpr int NP = 0;
@@ -203,14 +206,15 @@ struct F3Exp {
     static constexpr int NP = 0;
     static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return fm::exp(x + y + z); }
-    template <class T, bool FAST, int N>
+    template <class T, bool FAST, int N, int MODE>
     static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T*, T (&f)[N])
     {
         T a[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) a[i] = x[i] + y[i] + z[i];
-        exp_n<N>(a, f);
+        exp_n<N, MODE>(a, f);
     }
+    template <class T> static __device__ __forceinline__ T exp_arg_bound(T reach, const T*) { return reach; }
 };
 struct F3X2Y2Z2 {
     static constexpr int NP = 0;

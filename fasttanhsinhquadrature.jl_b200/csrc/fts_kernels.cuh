@@ -89,31 +89,31 @@ template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP
 template <class F, class = void> struct HasEvalN { static constexpr bool value = false; };
 template <class F> struct HasEvalN<F, decltype((void)F::HAS_EVALN)> { static constexpr bool value = F::HAS_EVALN; };
 
-template <class T, class F, bool FAST, int N> __device__ __forceinline__ void eval1d_n(const T (&x)[N], const T* p, T (&f)[N])
+template <class T, class F, bool FAST, int N, int MODE = 0> __device__ __forceinline__ void eval1d_n(const T (&x)[N], const T* p, T (&f)[N])
 {
     if constexpr (HasEvalN<F>::value) {
-        F::template evaln<T, FAST, N>(x, p, f);
+        F::template evaln<T, FAST, N, MODE>(x, p, f);
     } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], p);
     }
 }
 
-template <class T, class F, bool FAST, int N>
+template <class T, class F, bool FAST, int N, int MODE = 0>
 __device__ __forceinline__ void eval2d_n(const T (&x)[N], const T (&y)[N], const T* p, T (&f)[N])
 {
     if constexpr (HasEvalN<F>::value) {
-        F::template evaln<T, FAST, N>(x, y, p, f);
+        F::template evaln<T, FAST, N, MODE>(x, y, p, f);
     } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], y[i], p);
     }
 }
-template <class T, class F, bool FAST, int N>
+template <class T, class F, bool FAST, int N, int MODE = 0>
 __device__ __forceinline__ void eval3d_n(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T* p, T (&f)[N])
 {
     if constexpr (HasEvalN<F>::value) {
-        F::template evaln<T, FAST, N>(x, y, z, p, f);
+        F::template evaln<T, FAST, N, MODE>(x, y, z, p, f);
     } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], y[i], z[i], p);
@@ -164,6 +164,8 @@ template <class T> __device__ __forceinline__ bool quad_edge_axis(T& lo, T& hi, 
 // integrate1D(f, low, up, x, w, h)   /root/reference/src/integrate1D.jl:90-102
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_fixed1d_tpi(const Args<T> a)
 {
+    constexpr int MODE = (HasEvalN<F>::value && sizeof(T) == 8) ? EXP_SMEM : 0;   // dd has sizeof 16, float 4
+    if constexpr (MODE != 0) exp_tab_init();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -186,7 +188,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
             xs[2 * k + 1] = x0 + d;
             ws[k] = nd.w;
         }
-        eval1d_n<T, F, FAST, 2 * PAIRS>(xs, p, fs);
+        eval1d_n<T, F, FAST, 2 * PAIRS, MODE>(xs, p, fs);
 #pragma unroll
         for (int k = 0; k < PAIRS; ++k) s = muladd<T, FAST>(ws[k], fs[2 * k] + fs[2 * k + 1], s);
     }
@@ -291,24 +293,16 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
 
 // =================================================================== adaptive, reference order
 // adaptive_integrate_1D typed core   /root/reference/src/adaptive.jl:28-75
-template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_adaptive1d_tpi(const Args<T> a)
+// compile-time helpers for the exp fast paths (fts_math.cuh): only Float64 uses the table
+template <class T> struct IsF64 { static constexpr bool value = false; };
+template <> struct IsF64<double> { static constexpr bool value = true; };
+template <class T, class F> struct UsesExpTab { static constexpr bool value = HasEvalN<F>::value && IsF64<T>::value; };
+
+// levels of one integral; MODE selects the exp variant (shared-memory table, no range test)
+template <class T, class F, bool FAST, int MODE>
+__device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long long b, const T* p, T dx, T x0, bool neg, int flags)
 {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.batch) return;
-    T p[F::NP > 0 ? F::NP : 1];
-    load_params<F::NP>(p, a, b);
     const T half = num<T>::half();
-    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
-    bool neg = false;
-    int flags = 0;
-    if (a.options & OPT_QUAD_EDGE) {
-        if (!quad_edge_axis(lo, hi, neg)) {
-            store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
-            return;
-        }
-        if (neg) flags |= FLAG_FLIPPED;
-    }
-    const T dx = half * (hi - lo), x0 = half * (hi + lo);
     T h = a.tm * half;
     const T w0 = num<T>::pi() * half;
     T s_total;
@@ -316,7 +310,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
         const T d0 = dx * a.ix[0], d1 = dx * a.ix[1];
         const T xs[5] = {x0, d0 + x0, x0 - d0, d1 + x0, x0 - d1};
         T fs[5];
-        eval1d_n<T, F, FAST, 5>(xs, p, fs);
+        eval1d_n<T, F, FAST, 5, MODE>(xs, p, fs);
         s_total = w0 * fs[0];
         s_total = s_total + a.iw[0] * (fs[1] + fs[2]);
         s_total = s_total + a.iw[1] * (fs[3] + fs[4]);
@@ -337,7 +331,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
             const T d0 = dx * n0.x, d1 = dx * n1.x;
             const T xs[4] = {d0 + x0, x0 - d0, d1 + x0, x0 - d1};
             T fs[4];
-            eval1d_n<T, F, FAST, 4>(xs, p, fs);
+            eval1d_n<T, F, FAST, 4, MODE>(xs, p, fs);
             s_new = muladd<T, FAST>(n0.w, fs[0] + fs[1], s_new);
             s_new = muladd<T, FAST>(n1.w, fs[2] + fs[3], s_new);
         } else {
@@ -353,7 +347,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
                     xs[2 * k + 1] = x0 - d;
                     ws[k] = nd.w;
                 }
-                eval1d_n<T, F, FAST, 2 * PAIRS>(xs, p, fs);
+                eval1d_n<T, F, FAST, 2 * PAIRS, MODE>(xs, p, fs);
 #pragma unroll
                 for (int k = 0; k < PAIRS; ++k) s_new = muladd<T, FAST>(ws[k], fs[2 * k] + fs[2 * k + 1], s_new);
             }
@@ -375,6 +369,37 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
     }
     if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+}
+
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_adaptive1d_tpi(const Args<T> a)
+{
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // before any thread leaves (contains a barrier)
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    bool neg = false;
+    int flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        if (!quad_edge_axis(lo, hi, neg)) {
+            store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+            return;
+        }
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    if constexpr (UsesExpTab<T, F>::value) {
+        // every exp argument of this integral is bounded by F::exp_arg_bound(|x0|+|dx|): below 700
+        // the overflow/underflow test of exp is dead weight
+        if (F::template exp_arg_bound<T>(fm::abs(x0) + fm::abs(dx), p) < 700.0)
+            adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM | EXP_SAFE>(a, b, p, dx, x0, neg, flags);
+        else
+            adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM>(a, b, p, dx, x0, neg, flags);
+    } else {
+        adaptive1d_tpi_levels<T, F, FAST, 0>(a, b, p, dx, x0, neg, flags);
+    }
 }
 
 // adaptive_integrate_1D_cmpl typed core   /root/reference/src/adaptive.jl:727-785
