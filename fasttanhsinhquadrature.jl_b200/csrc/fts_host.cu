@@ -464,12 +464,16 @@ static const void* integrand_kernel(fts_integrand f, int dtype, int kid, int fas
 template <class T> static T load_elem(const void* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 static double elem_hi(int dtype, const void* p) { return dtype == FTS_F32 ? (double)load_elem<float>(p) : load_elem<double>(p); }
 
+// dynamic shared memory a kernel may ask for: the opt-in maximum minus what the kernels declare
+// statically (reduction scratch, flags, the 4 KiB exp table region)
+static size_t dyn_smem_limit() { return (size_t)g_prop.sharedMemPerBlockOptin - 8192; }
+
 static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, void* args, cudaStream_t s)
 {
-    if (smem > 48 * 1024) {
-        if (smem > (size_t)g_prop.sharedMemPerBlockOptin)
+    if (smem > 40 * 1024) {
+        if (smem > dyn_smem_limit())
             return set_error(FTS_ERR_UNSUPPORTED, "level needs " + std::to_string(smem) + " B of shared memory per CTA (max " +
-                                                      std::to_string(g_prop.sharedMemPerBlockOptin) + ")");
+                                                      std::to_string(dyn_smem_limit()) + ")");
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -480,6 +484,18 @@ static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, voi
     FTS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(block), params, smem, s));
     g_launches.fetch_add(1);
     return FTS_OK;
+}
+
+// threads per CTA of the thread-per-integral kernels (FTS_B200_TPI_BLOCK overrides the 1D value
+// for experiments; must not exceed the kernels' __launch_bounds__)
+static int tpi_block(int dim)
+{
+    static const int env1d = [] {
+        const char* e = getenv("FTS_B200_TPI_BLOCK");
+        const int v = e ? atoi(e) : 0;
+        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 256;
+    }();
+    return dim == 1 ? env1d : 128;
 }
 
 static int launch(const void* fn, long long threads, int block, void* args, cudaStream_t s)
@@ -524,7 +540,7 @@ static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, 
     const int dim = kind_dim(f->kind);
     const void* fn_cta = t->dtype == FTS_DD64 ? nullptr : integrand_kernel(f, t->dtype, KID_FIXED_CTA, 1);
     const size_t smem = dim == 1 ? 0 : (size_t)(dim == 2 ? 5 : 7) * t->n * sizeof(T);
-    const bool cta_ok = fn_cta && smem <= (size_t)g_prop.sharedMemPerBlockOptin;
+    const bool cta_ok = fn_cta && smem <= dyn_smem_limit();
     Style st = pick_style(order, dim, batch, 0, cta_ok, false);
     fts::Args<T> a;
     memset(&a, 0, sizeof a);
@@ -540,7 +556,7 @@ static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, 
     const int fast = order == FTS_ORDER_REFERENCE ? 0 : (order == FTS_ORDER_FAST ? 1 : 0);
     const void* fn = integrand_kernel(f, t->dtype, KID_FIXED_TPI, fast);
     if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no fixed-grid kernel built for this integrand/dtype/order");
-    return launch(fn, batch, dim == 1 ? 256 : 128, &a, s);
+    return launch(fn, batch, tpi_block(dim), &a, s);
 }
 
 static int check_fixed(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bstride, const void* params,
@@ -745,8 +761,8 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     const void* fn_grid = (is_dd || dim == 1) ? nullptr : integrand_kernel(f, c->dtype, KID_LEVEL_GRID, 1);
     const size_t nmax = max_levels > 0 ? ((size_t)2 << max_levels) : 2;
     const size_t smem_cta = dim == 1 ? 0 : (dim == 3 ? 7 : (cmpl ? 9 : 5)) * nmax * sizeof(T);
-    const bool cta_ok = fn_cta && smem_cta <= (size_t)g_prop.sharedMemPerBlockOptin;
-    const bool grid_ok = fn_grid && grid_level_smem(dim, cmpl, max_levels, sizeof(T)) <= (size_t)g_prop.sharedMemPerBlockOptin;
+    const bool cta_ok = fn_cta && smem_cta <= dyn_smem_limit();
+    const bool grid_ok = fn_grid && grid_level_smem(dim, cmpl, max_levels, sizeof(T)) <= dyn_smem_limit();
     Style st = pick_style(order, dim, batch, max_levels, cta_ok, grid_ok);
     if (st == STYLE_GRID)
         return run_adaptive_grid<T>(fn_grid, c, f, options, (const T*)low, (const T*)up, bstride, (const T*)params, pstride, load_elem<T>(rtol),
@@ -780,7 +796,7 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
         a.ticket = (unsigned int*)(queue + 1);
         a.tail_idx = queue + 2;
     }
-    if (int rc = launch(fn, batch, dim == 1 ? 256 : 128, &a, s)) return rc;
+    if (int rc = launch(fn, batch, tpi_block(dim), &a, s)) return rc;
     if (fn_tail) {
         const long long cap = (long long)g_prop.multiProcessorCount * 8;
         if (int rc = launch_raw(fn_tail, (unsigned)(batch < cap ? batch : cap), 256, 0, &a, s)) return rc;

@@ -371,7 +371,7 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
 }
 
-template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_adaptive1d_tpi(const Args<T> a)
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_tpi(const Args<T> a)
 {
     if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // before any thread leaves (contains a barrier)
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -216,7 +216,7 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ T cell2(const 
     } else if constexpr (HasEvalN<F>::value) {
         const T xs[4] = {xp, xm, xp, xm}, ys[4] = {yp, yp, ym, ym};
         T v[4];
-        eval2d_n<T, F, true, 4>(xs, ys, p, v);
+        eval2d_n<T, F, true, 4, UsesExpTab<T, F>::value ? EXP_SMEM : 0>(xs, ys, p, v);
         f = (v[0] + v[1]) + (v[2] + v[3]);
     } else {
         f = (F::template eval<T, true>(xp, yp, p) + F::template eval<T, true>(xm, yp, p)) +
@@ -276,6 +276,7 @@ extern __shared__ __align__(16) unsigned char fts_dyn_smem[];
 // adaptive_integrate_2D_avx (+ tensor-complement extension)   adaptive.jl:242-333
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive2d_cta(const Args<T> a)
 {
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
     constexpr bool CMPL = is_cmpl2d<F>::value;
     __shared__ T red[64];
     __shared__ int s_done;
@@ -345,6 +346,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
 // integrate2D_avx   integrate2D.jl:46-73
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed2d_cta(const Args<T> a)
 {
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
     __shared__ T red[64];
     const long long b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -403,7 +405,7 @@ template <class T, class F> __device__ __forceinline__ T cell3(const Sm3<T>& s, 
     if constexpr (HasEvalN<F>::value) {
         const T xs[8] = {xp, xm, xp, xm, xp, xm, xp, xm}, ys[8] = {yp, yp, ym, ym, yp, yp, ym, ym}, zs[8] = {zp, zp, zp, zp, zm, zm, zm, zm};
         T v[8];
-        eval3d_n<T, F, true, 8>(xs, ys, zs, p, v);
+        eval3d_n<T, F, true, 8, UsesExpTab<T, F>::value ? EXP_SMEM : 0>(xs, ys, zs, p, v);
         f = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     } else {
         f = ((FTS_FE(xp, yp, zp) + FTS_FE(xm, yp, zp)) + (FTS_FE(xp, ym, zp) + FTS_FE(xm, ym, zp))) +
@@ -422,7 +424,7 @@ template <class T, class F> __device__ __forceinline__ T plane3(const Sm3<T>& s,
         const T ys[12] = {ypj, ypj, ymj, ymj, y0, y0, y0, y0, ypi, ymi, ypi, ymi};
         const T zs[12] = {z0, z0, z0, z0, zpj, zpj, zmj, zmj, zpj, zpj, zmj, zmj};
         T v[12];
-        eval3d_n<T, F, true, 12>(xs, ys, zs, p, v);
+        eval3d_n<T, F, true, 12, UsesExpTab<T, F>::value ? EXP_SMEM : 0>(xs, ys, zs, p, v);
         f = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) + ((v[8] + v[9]) + (v[10] + v[11]));
     } else {
         f = ((FTS_FE(xp, ypj, z0) + FTS_FE(xm, ypj, z0)) + (FTS_FE(xp, ymj, z0) + FTS_FE(xm, ymj, z0))) +
@@ -508,6 +510,7 @@ __device__ __forceinline__ T level_sum_3d(const Sm3<T>& s, const T* p, int n, in
 // adaptive_integrate_3D_avx   adaptive.jl:489-706
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive3d_cta(const Args<T> a)
 {
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
     __shared__ T red[64];
     __shared__ int s_done;
     const long long b = blockIdx.x;
@@ -568,6 +571,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
 // integrate3D_avx   integrate3D.jl:68-123
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed3d_cta(const Args<T> a)
 {
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
     __shared__ T red[64];
     const long long b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -600,6 +604,7 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
     __shared__ T red[64];
     __shared__ int s_last;
     if (a.state && a.state[5] != num<T>::zero()) return;  // converged at an earlier level
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();
     const int tid = threadIdx.x;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, 0);
