@@ -107,6 +107,20 @@ def device_info() -> dict:
     return dict(device=dev.value, sm_count=sm.value, cc=(ma.value, mi.value), global_mem=mem.value)
 
 
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked, device-mapped host memory (fts_host_alloc).  Per-integral operands
+    and result arrays that live here are read and written IN PLACE by the kernels over PCIe
+    (fts_integrate_batch / fts_adaptive_batch take no staging copy); freed with the array."""
+    import weakref
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    ptr = C.c_void_p()
+    L.check(L.lib.fts_host_alloc(C.byref(ptr), max(n, 1)))
+    buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+    weakref.finalize(buf, L.lib.fts_host_free, C.c_void_p(ptr.value))
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+
 def launch_count(reset: bool = False) -> int:
     return int(L.lib.fts_launch_count(int(reset)))
 

@@ -149,7 +149,10 @@ int fts_shutdown(void);
 int fts_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, size_t* global_mem);
 /* Copies the calling thread's last error message; returns the full message length. */
 size_t fts_last_error(char* buf, size_t len);
-/* pinned host staging buffers for the e2e path (optional; any host pointer is accepted) */
+/* Pinned, device-mapped host memory (cudaMallocHost).  Optional — every host entry point accepts
+   any host pointer — but per-integral operands and result arrays that live in pinned memory
+   (from here or cudaHostRegister) are read and written IN PLACE by the kernels over PCIe, with no
+   staging copy; pageable buffers are staged through device scratch (chunked copy pipeline). */
 int fts_host_alloc(void** ptr, size_t bytes);
 int fts_host_free(void* ptr);
 

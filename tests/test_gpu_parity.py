@@ -159,6 +159,72 @@ def test_config_b_full_size_properties(gpu):
     assert same.mean() > 0.999 and rel(rf.value[same], r.value[same]).max() <= RTOL64
 
 
+def test_pinned_host_buffers_in_place_match_staged(gpu):
+    """fts_adaptive_batch / fts_integrate_batch on pinned host buffers (operands read and results
+    written in place by the kernels) against the same calls on pageable buffers (staged through
+    device scratch): bit-identical values, errors, levels and flags; broadcast and per-integral bounds."""
+    import ctypes as C
+    from fts_b200 import _lib as L
+    n = 300_007  # three chunks of the staged-input pipeline
+    a = _alpha(n)
+    cache = gpu.adaptive_cache_1D(np.float64, max_levels=16)
+    f = gpu.builtin("gauss")
+    lo1, hi1 = np.array([-1.0]), np.array([1.0])
+    rng = np.random.default_rng(5)
+    lon, hin = -1.0 - rng.random(n), 1.0 + rng.random(n)
+
+    def run(alloc, lo_src, hi_src, bstride):
+        lo, hi, al = alloc(lo_src.shape), alloc(hi_src.shape), alloc(n)
+        lo[...], hi[...], al[...] = lo_src, hi_src, a
+        v, e = alloc(n), alloc(n)
+        lv, fl = alloc(n, np.int32), alloc(n, np.int32)
+        gpu.adaptive_batch_host(cache, f, low=lo.ctypes.data, up=hi.ctypes.data, bounds_stride=bstride, params=al.ctypes.data, params_stride=1,
+                                rtol=1e-10, atol=0.0, max_levels=16, batch=n, value=v.ctypes.data, err=e.ctypes.data, levels=lv.ctypes.data,
+                                flags=fl.ctypes.data, order="reference", options=L.OPT_QUAD_EDGE_RULES)
+        return v.copy(), e.copy(), lv.copy(), fl.copy()
+
+    pageable = lambda shape, dt=np.float64: np.empty(shape, dt)
+    for lo_src, hi_src, bstride in ((lo1, hi1, 0), (lon, hin, 1)):
+        got = run(gpu.pinned_empty, lo_src, hi_src, bstride)
+        want = run(pageable, lo_src, hi_src, bstride)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        assert (got[3] & L.FLAG_CONVERGED).all()
+    from scipy.special import erf
+    assert rel(run(gpu.pinned_empty, lo1, hi1, 0)[0], np.sqrt(PI / a) * erf(np.sqrt(a))).max() < 1e-10
+
+    # integrals that go through the deep-level tail kernel (its parked state lives in `value`)
+    p0 = np.concatenate([np.full(300, 25.0), 10.0 ** np.linspace(3, 7, 9), np.full(300, 4.0)])
+    fr = gpu.builtin("runge")
+
+    def run_tail(alloc):
+        m = p0.shape[0]
+        lo, hi, al, v, lv = alloc(1), alloc(1), alloc(m), alloc(m), alloc(m, np.int32)
+        lo[...], hi[...], al[...] = -1.0, 1.0, p0
+        gpu.adaptive_batch_host(cache, fr, low=lo.ctypes.data, up=hi.ctypes.data, bounds_stride=0, params=al.ctypes.data, params_stride=1,
+                                rtol=1e-10, atol=0.0, max_levels=16, batch=m, value=v.ctypes.data, levels=lv.ctypes.data, order="reference")
+        return v.copy(), lv.copy()
+
+    (vt, lt), (vs_, ls_) = run_tail(gpu.pinned_empty), run_tail(pageable)
+    assert lt.max() >= 10 and np.array_equal(vt, vs_) and np.array_equal(lt, ls_)
+
+    # fixed grid through fts_integrate_batch
+    x, w, h = gpu.tanhsinh(np.float64, 80)
+    handle = gpu.api._tables.get(x, w, h)
+    fe = gpu.builtin("exp")
+
+    def run_fixed(alloc):
+        lo, hi, v = alloc(n), alloc(n), alloc(n)
+        lo[...], hi[...] = lon, hin
+        L.check(L.lib.fts_integrate_batch(handle, fe._h, L.ORDER_REFERENCE, C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data), 1, None, 0, n,
+                                          C.c_void_p(v.ctypes.data)))
+        return v.copy()
+
+    vp, vs = run_fixed(gpu.pinned_empty), run_fixed(pageable)
+    assert np.array_equal(vp, vs)
+    assert rel(vp, np.exp(hin) - np.exp(lon)).max() < 1e-13
+
+
 def test_fast_cta_1d_matches_exact_sum(gpu, oracle):
     """small batch -> one CTA per integral (k_adaptive1d_cta); compare with the exactly-summed oracle"""
     a = _alpha(64)

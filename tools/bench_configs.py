@@ -54,6 +54,31 @@ def case_a(reps):
                  gevals_per_s=evals / t / 1e9, fp64_frac_nominal=evals / t * 32.5 / 1e12 / FP64_PEAK, max_rel_err_vs_exact=err)
 
 
+def case_apin(reps):
+    """config A through fts_integrate_batch on PINNED host buffers (bounds read and values written in place over PCIe)"""
+    import ctypes as C
+    from fts_b200 import _lib as L, api
+    n = 1 << 20
+    low, up, out = fts.pinned_empty(n), fts.pinned_empty(n), fts.pinned_empty(n)
+    up[...] = 1.0 + np.arange(n) * 2.0 ** -20
+    low[...] = 0.0
+    f = fts.builtin("exp")
+    for N in (80, 256, 1024):
+        x, w, h = fts.tanhsinh(np.float64, N)
+        handle = api._tables.get(x, w, h)
+        for order in ("reference", "fast"):
+            def call():
+                L.check(L.lib.fts_integrate_batch(handle, f._h, api._order(order), C.c_void_p(low.ctypes.data), C.c_void_p(up.ctypes.data), 1, None, 0,
+                                                  n, C.c_void_p(out.ctypes.data)))
+                return out
+            t, v = best_of(call, reps)
+            evals = n * (2 * (N // 2) + 1)
+            err = float(np.max(np.abs(v - (np.exp(up) - 1)) / (np.exp(up) - 1)))
+            emit(case="A-pinned-host", api="integrate1D" + ("_avx" if order == "fast" else ""), N=N, batch=n, ms=t * 1e3, integrals_per_s=n / t,
+                 gevals_per_s=evals / t / 1e9, fp64_frac_nominal=evals / t * 32.5 / 1e12 / FP64_PEAK, max_rel_err_vs_exact=err,
+                 pcie_bytes=24 * n)
+
+
 def case_adev(reps):
     """config A with inputs resident in HBM: kernel-only time (CUDA events), reference and FMA order"""
     import torch
@@ -192,7 +217,7 @@ def main():
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
     emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
     for c in args.cases.split(","):
-        {"A": case_a, "Adev": case_adev, "C": case_c, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
+        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
 
 
 if __name__ == "__main__":
