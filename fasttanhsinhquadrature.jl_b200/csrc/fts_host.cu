@@ -21,6 +21,9 @@ int fts_tg_fixed(int dtype, int N, int D, void* x, void* w, void* h);
 int fts_tg_cache1d(int dtype, int L, int complement, void* tm, void* ix, void* iw, void* ic, void* xs, void* ws, void* cs);
 int fts_tg_cache_tensor(int dtype, int D, int L, void* tm, void* ix, void* iw, void* xs, void* ws);
 int fts_tg_tensor_complements(int dtype, int L, const void* tm_in, void* ix, void* iw, void* ic, void* xs, void* ws, void* cs);
+int fts_tg_hopt(int dtype, int N, double d, void* out);
+int fts_tg_hmax(int dtype, int N, int D, void* out);
+long fts_tg_opt(int dtype, int N, double d, int D, long capacity, void* x, void* w, void* h);
 }
 
 // ------------------------------------------------------------------------------- errors ------
@@ -285,6 +288,28 @@ extern "C" int fts_tanhsinh(int dtype, int N, int D, void* x_out, void* w_out, v
     if (int rc = check_dtype(dtype)) return rc;
     if (N < 2 || D < 1) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_tanhsinh: N must be >= 2 and D >= 1");
     return fts_tg_fixed(dtype, N, D, x_out, w_out, h_out) ? set_error(FTS_ERR_INTERNAL, "fts_tanhsinh failed") : FTS_OK;
+}
+extern "C" int fts_hopt(int dtype, int N, double d, void* h_out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (N < 1 || !(d > 0) || !h_out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_hopt: N must be >= 1 and d > 0");
+    return fts_tg_hopt(dtype, N, d, h_out) ? set_error(FTS_ERR_INTERNAL, "fts_hopt failed") : FTS_OK;
+}
+extern "C" int fts_hmax(int dtype, int N, int D, void* h_out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (N < 2 || D < 1 || !h_out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_hmax: N must be >= 2 and D >= 1");
+    return fts_tg_hmax(dtype, N, D, h_out) ? set_error(FTS_ERR_INTERNAL, "fts_hmax failed") : FTS_OK;
+}
+extern "C" int fts_tanhsinh_opt(int dtype, int N, double d, int D, int64_t capacity, void* x_out, void* w_out, void* h_out, int64_t* count)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (N < 1 || D < 1 || !(d > 0) || capacity < 0 || !h_out || !count || (capacity > 0 && (!x_out || !w_out)))
+        return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_tanhsinh_opt: bad arguments");
+    const long k = fts_tg_opt(dtype, N, d, D, (long)capacity, x_out, w_out, h_out);
+    if (k < 0) return set_error(FTS_ERR_INTERNAL, "fts_tanhsinh_opt failed");
+    *count = k;
+    return FTS_OK;
 }
 extern "C" int fts_cache1d_generate(int dtype, int max_levels, int complement, void* tm_out, void* initial_x, void* initial_w,
                                     void* initial_c, void* xs_flat, void* ws_flat, void* cs_flat)

@@ -193,10 +193,82 @@ template <class T> void gen_cache_tensor(int D, int L, void* tm_out, void* ix, v
     }
 }
 
+// ---- optimal-spacing grids (core.jl:276-302) -------------------------------------------------
+// principal branch of Lambert W for z >= 0 (the reference calls LambertW.jl): Halley iteration
+template <class T> T lambert_w0(T z)
+{
+    if (!(z > (T)0)) return (T)0;
+    T w = z < (T)3 ? P<T>::log((T)1 + z) * (T)0.75 : P<T>::log(z) - P<T>::log(P<T>::log(z));
+    for (int it = 0; it < 60; ++it) {
+        const T e = P<T>::exp(w);
+        const T f = w * e - z;
+        const T w1 = w + (T)1;
+        const T step = f / (e * w1 - ((w + (T)2) * f) / (w1 + w1));
+        w = w - step;
+        if (P<T>::abs(step) <= P<T>::abs(w) * (T)1e-40) break;
+    }
+    return w;
+}
+// hopt(T, N, d) = (2/N) W(2 d N)   core.jl:289-291
+template <class T> T h_opt(int N, double d) { return ((T)2 / (T)N) * lambert_w0<T>((T)(d + d) * (T)N); }
+// hmax(T, N, D) = tmax(T,D) / (N div 2)   core.jl:293-302
+template <class T> T h_max(int N, int D) { return window<T>(0, D) / (T)(N / 2); }
+// number of points of the range h:h:tm (core.jl:285): k*h <= tm, with the half-ulp slack of
+// Julia's float ranges
+template <class T> long opt_count(T h, T tm)
+{
+    const q128 r = (q128)tm / (q128)h;
+    long k = (long)r;
+    if ((q128)(k + 1) - r < (q128)1e-9 * r) ++k;
+    return k;
+}
+template <class T> long gen_opt(int N, double d, int D, long capacity, void* x, void* w, void* h_out)
+{
+    const T tm = window<T>(0, D);
+    const T h = h_opt<T>(N, d);
+    Out<T>::put(h_out, 0, h);
+    if (!(h > (T)0)) return 0;
+    const long k = opt_count<T>(h, tm);
+    for (long i = 0; i < k && i < capacity; ++i) {
+        const T t = (T)((q128)(i + 1) * (q128)h);  // range element in twice the working precision
+        Out<T>::put(x, i, node_x<T>(t));
+        Out<T>::put(w, i, node_w<T>(t));
+    }
+    return k;
+}
+
 }  // namespace
 
 // entry points used by fts_host.cu (not part of the public ABI; the public wrappers validate)
 extern "C" {
+
+int fts_tg_hopt(int dtype, int N, double d, void* out)
+{
+    switch (dtype) {
+    case FTS_F32: Out<float>::put(out, 0, h_opt<float>(N, d)); return 0;
+    case FTS_F64: Out<double>::put(out, 0, h_opt<double>(N, d)); return 0;
+    case FTS_DD64: Out<q128>::put(out, 0, h_opt<q128>(N, d)); return 0;
+    }
+    return 1;
+}
+int fts_tg_hmax(int dtype, int N, int D, void* out)
+{
+    switch (dtype) {
+    case FTS_F32: Out<float>::put(out, 0, h_max<float>(N, D)); return 0;
+    case FTS_F64: Out<double>::put(out, 0, h_max<double>(N, D)); return 0;
+    case FTS_DD64: Out<q128>::put(out, 0, h_max<q128>(N, D)); return 0;
+    }
+    return 1;
+}
+long fts_tg_opt(int dtype, int N, double d, int D, long capacity, void* x, void* w, void* h)
+{
+    switch (dtype) {
+    case FTS_F32: return gen_opt<float>(N, d, D, capacity, x, w, h);
+    case FTS_F64: return gen_opt<double>(N, d, D, capacity, x, w, h);
+    case FTS_DD64: return gen_opt<q128>(N, d, D, capacity, x, w, h);
+    }
+    return -1;
+}
 
 int fts_tg_window(int dtype, int which, int D, void* out)
 {

@@ -60,6 +60,9 @@ _SIGS = {
     "fts_family_info": (ci, [ci, C.POINTER(ci), C.POINTER(ci)]),
     "fts_window": (ci, [ci, ci, ci, vp]),
     "fts_tanhsinh": (ci, [ci, ci, ci, vp, vp, vp]),
+    "fts_hopt": (ci, [ci, ci, C.c_double, vp]),
+    "fts_hmax": (ci, [ci, ci, ci, vp]),
+    "fts_tanhsinh_opt": (ci, [ci, ci, C.c_double, ci, i64, vp, vp, vp, C.POINTER(i64)]),
     "fts_cache1d_generate": (ci, [ci, ci, ci] + [vp] * 7),
     "fts_cache_tensor_generate": (ci, [ci, ci, ci] + [vp] * 5),
     "fts_cache_tensor_cmpl_generate": (ci, [ci, ci] + [vp] * 7),

@@ -283,6 +283,34 @@ def tanhsinh(T=np.float64, N: Optional[int] = None, D: int = 1):
     return x, w, h[0]
 
 
+def hopt(T=np.float64, N: int = 2, d: float = math.pi / 2):
+    """hopt(T, N, d) = (2/N) W(2dN) (core.jl:289-291)"""
+    dt = _dt(T)
+    out = np.zeros(1, dt)
+    L.check(L.lib.fts_hopt(_DT_CODE[dt], int(N), float(d), _ptr(out)))
+    return out[0]
+
+
+def hmax(T=np.float64, N: int = 2, D: int = 1):
+    """hmax(T, N, D) = tmax(T, D) / (N div 2) (core.jl:293-302)"""
+    dt = _dt(T)
+    out = np.zeros(1, dt)
+    L.check(L.lib.fts_hmax(_DT_CODE[dt], int(N), int(D), _ptr(out)))
+    return out[0]
+
+
+def tanhsinh_opt(T=np.float64, N: int = 2, d: float = math.pi / 2, D: int = 1):
+    """tanhsinh_opt(T, N, d; D) (core.jl:276-287): nodes at t = h:h:tmax(T,D) with the
+    optimal-spacing step h = hopt(T, N, d).  Returns (x, w, h)."""
+    dt = _dt(T)
+    h = np.zeros(1, dt)
+    count = C.c_int64()
+    L.check(L.lib.fts_tanhsinh_opt(_DT_CODE[dt], int(N), float(d), int(D), 0, None, None, _ptr(h), C.byref(count)))
+    x, w = np.zeros(count.value, dt), np.zeros(count.value, dt)
+    L.check(L.lib.fts_tanhsinh_opt(_DT_CODE[dt], int(N), float(d), int(D), count.value, _ptr(x), _ptr(w), _ptr(h), C.byref(count)))
+    return x, w, h[0]
+
+
 class _TableCache:
     """device copies of (x,w,h) triples handed to integrate*D, keyed by the host arrays' identity"""
 

@@ -161,6 +161,15 @@ int fts_host_free(void* ptr);
 int fts_window(int dtype, int which, int D, void* tm_out);
 /* tanhsinh(T, N; D)  (core.jl:256-267): n = N div 2 nodes; x_out,w_out hold n elements, h_out one. */
 int fts_tanhsinh(int dtype, int N, int D, void* x_out, void* w_out, void* h_out);
+/* hopt(T, N, d) = (2/N) W(2dN), W = Lambert W (core.jl:289-291); hmax(T, N, D) = tmax(T,D)/(N div 2)
+   (core.jl:293-302).  One element of the dtype is written. */
+int fts_hopt(int dtype, int N, double d, void* h_out);
+int fts_hmax(int dtype, int N, int D, void* h_out);
+/* tanhsinh_opt(T, N, d; D) (core.jl:276-287): nodes at t = h, 2h, ... <= tmax(T,D) with h = hopt.
+   *count receives the number of nodes; at most `capacity` of them are written (call with
+   capacity 0 to size the buffers). */
+int fts_tanhsinh_opt(int dtype, int N, double d, int D, int64_t capacity,
+                     void* x_out, void* w_out, void* h_out, int64_t* count);
 /* _build_adaptive_1d_cache (caches.jl:59-91): flat level arrays of 2^(L+1)-2 elements
    (level l at offset 2^l-2, l=1..L), complement!=0 selects the t_w_max window. */
 int fts_cache1d_generate(int dtype, int max_levels, int complement, void* tm_out,

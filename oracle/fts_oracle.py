@@ -339,3 +339,24 @@ class Oracle:
             _ptr(cache["xs"]), _ptr(cache["ws"]), _ptr(cache["cs"]), C.c_long(batch), _ptr(value), _ptr(err),
             _ptr(level), _ptr(conv), _ptr(evals), nthreads)
         return dict(value=value, err=err, level=level, converged=conv.astype(bool), evals=evals)
+
+
+# ---------------------------------------------------------------------- optimal-spacing grids --
+def hopt_ref(N: int, d: float = np.pi / 2) -> float:
+    """hopt(Float64, N, d) = (2/N) * lambertw(2dN)   src/core.jl:289-291 (LambertW.jl -> scipy)"""
+    from scipy.special import lambertw
+    return float(2.0 / N * lambertw(2.0 * d * N).real)
+
+
+def tanhsinh_opt_ref(N: int, d: float = np.pi / 2, tm: float = None):
+    """tanhsinh_opt(Float64, N, d)   src/core.jl:276-287: t = h:h:tm, x = ordinate.(t), w = weight.(t)
+    with ordinate/weight as in src/core.jl:126-185 (clamp to prevfloat(1); weight 0 beyond 700)."""
+    h = hopt_ref(N, d)
+    k = int(np.floor(tm / h * (1 + 1e-12)))
+    t = h * np.arange(1, k + 1)
+    u = (np.pi / 2) * np.sinh(t)
+    lim = np.nextafter(1.0, 0.0)
+    x = np.clip(np.tanh(u), -lim, lim)
+    with np.errstate(over="ignore"):
+        w = np.where(np.abs(u) > 700.0, 0.0, (np.pi / 2) * np.cosh(t) / np.cosh(u) ** 2)
+    return x, w, h

@@ -158,3 +158,27 @@ def test_double64_helpers(fts):
     assert abs(back[1] - mpmath.mpf("1e-30")) < mpmath.mpf("1e-60")
     b = fts.to_dd([1.5, -2.0])
     assert np.array_equal(b["hi"], [1.5, -2.0]) and np.array_equal(b["lo"], [0.0, 0.0])
+
+
+def test_optimal_spacing_grids(fts, oracle):
+    """tanhsinh_opt / hopt / hmax (core.jl:276-302; KATs of test/core.jl:59-69) against the numpy
+    restatement in oracle/fts_oracle.py"""
+    import fts_oracle
+    for N in (80, 81, 16, 1000):
+        x, w, h = fts.tanhsinh_opt(np.float64, N)
+        assert len(x) == len(w) and h > 0                                  # test/core.jl:60-66
+        xr, wr, hr = fts_oracle.tanhsinh_opt_ref(N, tm=float(fts.tmax(np.float64)))
+        assert abs(h - hr) <= 2e-16 * hr and len(x) == len(xr)
+        assert np.max(np.abs(x - xr)) <= 4e-16 and np.max(np.abs(w - wr) / np.maximum(wr, 1e-300)) <= 5e-14
+        assert fts.hopt(np.float64, N) == h and fts.hmax(np.float64, N) == fts.tmax(np.float64) / (N // 2)
+    # W(z) e^{W(z)} = z in every precision
+    for T, tol in ((np.float32, 3e-7), (np.float64, 5e-16)):
+        hh = float(fts.hopt(T, 80))
+        wv = hh * 80 / 2
+        assert abs(wv * math.exp(wv) - math.pi * 80) <= tol * math.pi * 80 * 8
+    hi, lo = fts.hopt(fts.Double64, 80)
+    assert abs(hi - float(fts.hopt(np.float64, 80))) <= 1e-16 and abs(lo) < 1e-17
+    # the grid integrates: exp on [-1,1] (spacing is optimal for N points, error ~1e-15)
+    x, w, h = fts.tanhsinh_opt(np.float64, 80)
+    val = h * (math.pi / 2 + float(np.sum(w * (np.exp(x) + np.exp(-x)))))
+    assert abs(val - (math.e - 1 / math.e)) < 1e-14
