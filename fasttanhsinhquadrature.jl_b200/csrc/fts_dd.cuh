@@ -117,7 +117,7 @@ FTS_HD dd dd_exp(dd a)
 {
     const dd LN2(6.931471805599452862e-01, 2.319046813846299558e-17);
     if (a.hi != a.hi) return dd(a.hi);
-    if (a.hi <= -709.0) return dd(0.0);
+    if (a.hi < -745.2) return dd(0.0);  // down to the smallest subnormal (ldexp below rounds once)
     if (a.hi >= 709.0) return dd(dd_inf());
     if (a.hi == 0.0 && a.lo == 0.0) return dd(1.0);
     double kf = ::floor(a.hi / LN2.hi + 0.5);

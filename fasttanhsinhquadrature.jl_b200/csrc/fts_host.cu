@@ -11,6 +11,7 @@
 
 #include "fts_internal.h"
 #include "fts_kernels_cta.cuh"
+#include "fts_tablegen_dev.cuh"
 
 using namespace fts_host;
 
@@ -436,6 +437,137 @@ extern "C" int fts_cache_tensor_cmpl_upload(int dtype, int max_levels, const voi
 {
     return make_cache(dtype, 2, 1, max_levels, tm, initial_x, initial_w, initial_c, xs_flat, ws_flat, cs_flat, out);
 }
+// ---- on-device generation and download ----------------------------------------
+template <class T> static int tables_create_dev(int N, int D, fts_tables_s* t)
+{
+    const int n = N / 2;  // core.jl:257
+    T tm;
+    fts_tg_window(t->dtype, 0, D, &tm);
+    const T h = tm / T((double)n);
+    memset(t->h, 0, sizeof t->h);
+    memcpy(t->h, &h, sizeof(T));
+    t->n = n;
+    t->d_grid = nullptr;
+    if (n == 0) return FTS_OK;
+    FTS_CUDA(cudaMalloc(&t->d_grid, sizeof(fts::Node<T>) * n));
+    fts::k_tablegen_fixed<T><<<(n + 127) / 128, 128, 0, g_stream>>>((fts::Node<T>*)t->d_grid, n, h, tm);
+    FTS_CUDA(cudaGetLastError());
+    FTS_CUDA(cudaStreamSynchronize(g_stream));
+    return FTS_OK;
+}
+
+extern "C" int fts_tables_fixed_create(int dtype, int N, int D, fts_tables* out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (N < 2 || D < 1 || !out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_tables_fixed_create: N must be >= 2 and D >= 1");
+    if (int rc = ensure_init()) return rc;
+    fts_tables_s* t = new fts_tables_s();
+    t->dtype = dtype;
+    int rc = dtype == FTS_F32 ? tables_create_dev<float>(N, D, t) : dtype == FTS_F64 ? tables_create_dev<double>(N, D, t) : tables_create_dev<fts::dd>(N, D, t);
+    if (rc) { if (t->d_grid) cudaFree(t->d_grid); delete t; return rc; }
+    *out = t;
+    return FTS_OK;
+}
+
+template <class T> static int cache_create_dev(fts_cache_s* c, const void* tm_in)
+{
+    T tm;
+    memcpy(&tm, tm_in, sizeof(T));
+    memset(c->tm, 0, sizeof c->tm); memset(c->ix, 0, sizeof c->ix); memset(c->iw, 0, sizeof c->iw); memset(c->ic, 0, sizeof c->ic);
+    memcpy(c->tm, &tm, sizeof(T));
+    T* d_init = nullptr;
+    FTS_CUDA(cudaMalloc((void**)&d_init, 6 * sizeof(T)));
+    fts::k_tablegen_initial<T><<<1, 32, 0, g_stream>>>(d_init, tm);
+    T init[6];
+    cudaError_t e = cudaMemcpyAsync(init, d_init, sizeof init, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    cudaFree(d_init);
+    FTS_CUDA(e);
+    memcpy(c->ix, init, 2 * sizeof(T)); memcpy(c->iw, init + 2, 2 * sizeof(T));
+    if (c->kind == 1) memcpy(c->ic, init + 4, 2 * sizeof(T));
+    c->d_nodes = nullptr; c->d_nodes_c = nullptr;
+    if (c->count == 0) return FTS_OK;
+    FTS_CUDA(cudaMalloc(&c->d_nodes, sizeof(fts::Node<T>) * c->count));
+    if (c->kind == 1) FTS_CUDA(cudaMalloc(&c->d_nodes_c, sizeof(fts::NodeC<T>) * c->count));
+    const unsigned blocks = (unsigned)((c->count + 127) / 128);
+    fts::k_tablegen_levels<T><<<blocks, 128, 0, g_stream>>>((fts::Node<T>*)c->d_nodes, (fts::NodeC<T>*)c->d_nodes_c, c->count, tm, c->D != 0);
+    FTS_CUDA(cudaGetLastError());
+    FTS_CUDA(cudaStreamSynchronize(g_stream));
+    return FTS_OK;
+}
+
+// D = 0: 1D cache (kind 0 regular / 1 complement); D = 2, 3: tensor cache; D = 2 with kind 1: the
+// 2D complement table (window t_w_max(T, 2), see fts_cache_tensor_cmpl_generate)
+extern "C" int fts_cache_create(int dtype, int D, int kind, int max_levels, fts_cache* out)
+{
+    if (int rc = check_dtype(dtype)) return rc;
+    if (!out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_cache_create: null output");
+    if (max_levels < 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "`max_levels` must be nonnegative.");  // caches.jl:60,149
+    if (max_levels > 28) return set_error(FTS_ERR_INVALID_ARGUMENT, "max_levels > 28 is not supported");
+    if ((D != 0 && D != 2 && D != 3) || (kind != 0 && kind != 1) || (kind == 1 && D == 3))
+        return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_cache_create: D must be 0 (1D), 2 or 3; complement tables exist for D = 0 and 2");
+    if (int rc = ensure_init()) return rc;
+    unsigned char tm[16];
+    memset(tm, 0, sizeof tm);
+    // windows: caches.jl:47-48 (1D), :152 (tensor); scalar Newton iterations stay on the host
+    if (D == 0) fts_tg_window(dtype, kind == 1 ? 2 : 0, 1, tm);
+    else if (kind == 1) fts_tg_window(dtype, 2, 2, tm);
+    else fts_tg_window(dtype, 0, D, tm);
+    fts_cache_s* c = new fts_cache_s();
+    c->dtype = dtype; c->D = D; c->kind = kind; c->max_levels = max_levels;
+    c->count = D == 0 ? ((2LL << max_levels) - 2) : ((4LL << max_levels) - 4);
+    int rc = dtype == FTS_F32 ? cache_create_dev<float>(c, tm) : dtype == FTS_F64 ? cache_create_dev<double>(c, tm) : cache_create_dev<fts::dd>(c, tm);
+    if (rc) { if (c->d_nodes) cudaFree(c->d_nodes); if (c->d_nodes_c) cudaFree(c->d_nodes_c); delete c; return rc; }
+    *out = c;
+    return FTS_OK;
+}
+
+template <class T> static int download_nodes(const void* d_nodes, const void* d_nodes_c, long long count, void* x, void* w, void* cc)
+{
+    if (count == 0) return FTS_OK;
+    if (d_nodes_c && cc) {
+        std::vector<fts::NodeC<T>> h(count);
+        FTS_CUDA(cudaMemcpy(h.data(), d_nodes_c, sizeof(fts::NodeC<T>) * count, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < count; ++i) { if (x) ((T*)x)[i] = h[i].x; if (w) ((T*)w)[i] = h[i].w; ((T*)cc)[i] = h[i].c; }
+        return FTS_OK;
+    }
+    std::vector<fts::Node<T>> h(count);
+    FTS_CUDA(cudaMemcpy(h.data(), d_nodes, sizeof(fts::Node<T>) * count, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < count; ++i) { if (x) ((T*)x)[i] = h[i].x; if (w) ((T*)w)[i] = h[i].w; }
+    return FTS_OK;
+}
+
+// the flat level arrays of a cache, in the layout fts_cache*_upload takes (any pointer may be null)
+extern "C" int fts_cache_download(fts_cache c, void* tm, void* initial_x, void* initial_w, void* initial_c, void* xs_flat, void* ws_flat, void* cs_flat)
+{
+    if (!c) return set_error(FTS_ERR_INVALID_ARGUMENT, "null cache");
+    if (cs_flat && c->kind != 1) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_cache_download: not a complement cache");
+    const size_t es = dtype_size(c->dtype);
+    if (tm) memcpy(tm, c->tm, es);
+    if (initial_x) memcpy(initial_x, c->ix, 2 * es);
+    if (initial_w) memcpy(initial_w, c->iw, 2 * es);
+    if (initial_c) memcpy(initial_c, c->ic, 2 * es);
+    switch (c->dtype) {
+    case FTS_F32: return download_nodes<float>(c->d_nodes, c->d_nodes_c, c->count, xs_flat, ws_flat, cs_flat);
+    case FTS_F64: return download_nodes<double>(c->d_nodes, c->d_nodes_c, c->count, xs_flat, ws_flat, cs_flat);
+    case FTS_DD64: return download_nodes<fts::dd>(c->d_nodes, c->d_nodes_c, c->count, xs_flat, ws_flat, cs_flat);
+    }
+    return set_error(FTS_ERR_INTERNAL, "bad dtype");
+}
+extern "C" int fts_tables_download(fts_tables t, int* n, void* x, void* w, void* h)
+{
+    if (!t) return set_error(FTS_ERR_INVALID_ARGUMENT, "null tables");
+    if (n) *n = t->n;
+    if (h) memcpy(h, t->h, dtype_size(t->dtype));
+    if (!x && !w) return FTS_OK;
+    switch (t->dtype) {
+    case FTS_F32: return download_nodes<float>(t->d_grid, nullptr, t->n, x, w, nullptr);
+    case FTS_F64: return download_nodes<double>(t->d_grid, nullptr, t->n, x, w, nullptr);
+    case FTS_DD64: return download_nodes<fts::dd>(t->d_grid, nullptr, t->n, x, w, nullptr);
+    }
+    return set_error(FTS_ERR_INTERNAL, "bad dtype");
+}
+
 extern "C" int fts_cache_info(fts_cache c, int* dtype, int* D, int* kind, int* max_levels)
 {
     if (!c) return set_error(FTS_ERR_INVALID_ARGUMENT, "null cache");

@@ -6,7 +6,7 @@ Python host mirror of the reference's Julia API over the C ABI of libfts_b200.so
 from ._lib import (ArgumentError, DimensionMismatch, FtsError, LIB_PATH, FLAG_CONVERGED, FLAG_FLIPPED, FLAG_MAX_LEVELS,
                    FLAG_ZERO_WIDTH, KIND_1D, KIND_1D_CMPL, KIND_2D, KIND_2D_CMPL, KIND_3D, ORDER_AUTO, ORDER_FAST, ORDER_REFERENCE)
 from . import api, distributed
-from .api import (FAMILIES, AdaptiveCache, AdaptiveResult, ConvergenceWarning, Double64, Integrand, adaptive_cache_1D,
+from .api import (FAMILIES, AdaptiveCache, AdaptiveResult, DeviceTables, ConvergenceWarning, Double64, Integrand, adaptive_cache_1D,
                   adaptive_cache_2D, adaptive_cache_2D_cmpl, adaptive_cache_3D, adaptive_integrate_1D, adaptive_integrate_1D_avx,
                   adaptive_integrate_1D_cmpl, adaptive_integrate_1D_cmpl_avx, adaptive_integrate_2D, adaptive_integrate_2D_avx,
                   adaptive_integrate_2D_cmpl, adaptive_integrate_3D, adaptive_integrate_3D_avx, builtin, cuda_integrand, dd_to_mpf,

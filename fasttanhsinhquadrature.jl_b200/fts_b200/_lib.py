@@ -71,6 +71,10 @@ _SIGS = {
     "fts_cache1d_upload": (ci, [ci, ci, ci] + [vp] * 7 + [C.POINTER(vp)]),
     "fts_cache_tensor_upload": (ci, [ci, ci, ci] + [vp] * 5 + [C.POINTER(vp)]),
     "fts_cache_tensor_cmpl_upload": (ci, [ci, ci] + [vp] * 7 + [C.POINTER(vp)]),
+    "fts_tables_fixed_create": (ci, [ci, ci, ci, C.POINTER(vp)]),
+    "fts_cache_create": (ci, [ci, ci, ci, ci, C.POINTER(vp)]),
+    "fts_tables_download": (ci, [vp, C.POINTER(ci), vp, vp, vp]),
+    "fts_cache_download": (ci, [vp] + [vp] * 7),
     "fts_cache_info": (ci, [vp] + [C.POINTER(ci)] * 4),
     "fts_cache_free": (ci, [vp]),
     "fts_integrand_builtin": (ci, [ci, C.POINTER(vp)]),

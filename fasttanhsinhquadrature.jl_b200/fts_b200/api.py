@@ -527,33 +527,77 @@ def _build_cache(dt, D, kind, max_levels) -> AdaptiveCache:
     return AdaptiveCache(dt, D, kind, max_levels, tm[0], ix, iw, ic, xs, ws, cs)
 
 
-def _cache(dt, D, kind, max_levels) -> AdaptiveCache:
-    key = (dt.str if dt != Double64 else "dd", D, kind, int(max_levels))
+def _build_cache_on_device(dt, D, kind, max_levels) -> AdaptiveCache:
+    """fts_cache_create: the level tables are computed by a kernel straight into device memory;
+    the host copy behind `.xs/.ws/.cs` is a download of them."""
+    if max_levels < 0:
+        raise ArgumentError(L.ERR_INVALID_ARGUMENT, "`max_levels` must be nonnegative.")
+    code = _DT_CODE[dt]
+    h = C.c_void_p()
+    L.check(L.lib.fts_cache_create(code, D, kind, max_levels, C.byref(h)))
+    tot = ((2 << max_levels) - 2) if D == 0 else ((4 << max_levels) - 4)
+    tm = np.zeros(1, dt); ix = np.zeros(2, dt); iw = np.zeros(2, dt); ic = np.zeros(2, dt)
+    xs = np.zeros(tot, dt); ws = np.zeros(tot, dt)
+    cs = np.zeros(tot, dt) if (kind == 1 or D == 0) else None
+    want_c = kind == 1
+    L.check(L.lib.fts_cache_download(h, _ptr(tm), _ptr(ix), _ptr(iw), _ptr(ic) if want_c else None, _ptr(xs), _ptr(ws),
+                                     _ptr(cs) if want_c else None))
+    c = AdaptiveCache(dt, D, kind, max_levels, tm[0], ix, iw, ic, xs, ws, cs)
+    c._h = h
+    return c
+
+
+def _cache(dt, D, kind, max_levels, on_device: bool = False) -> AdaptiveCache:
+    key = (dt.str if dt != Double64 else "dd", D, kind, int(max_levels), bool(on_device))
     with _CACHES_LOCK:
         c = _CACHES.get(key)
         if c is None:
-            c = _CACHES[key] = _build_cache(dt, D, kind, int(max_levels))
+            c = _CACHES[key] = (_build_cache_on_device if on_device else _build_cache)(dt, D, kind, int(max_levels))
         return c
 
 
-def adaptive_cache_1D(T=np.float64, max_levels: int = 16, complement: bool = False) -> AdaptiveCache:
-    """adaptive_cache_1D(T; max_levels=16, complement=false)   caches.jl:120-123 (memoised)"""
-    return _cache(_dt(T), 0, 1 if complement else 0, max_levels)
+def adaptive_cache_1D(T=np.float64, max_levels: int = 16, complement: bool = False, on_device: bool = False) -> AdaptiveCache:
+    """adaptive_cache_1D(T; max_levels=16, complement=false)   caches.jl:120-123 (memoised).
+    on_device=True builds the tables with a kernel in HBM (fts_cache_create) instead of on the host."""
+    return _cache(_dt(T), 0, 1 if complement else 0, max_levels, on_device)
 
 
-def adaptive_cache_2D(T=np.float64, max_levels: int = 8) -> AdaptiveCache:
+def adaptive_cache_2D(T=np.float64, max_levels: int = 8, on_device: bool = False) -> AdaptiveCache:
     """adaptive_cache_2D(T; max_levels=8)   caches.jl:211-212"""
-    return _cache(_dt(T), 2, 0, max_levels)
+    return _cache(_dt(T), 2, 0, max_levels, on_device)
 
 
-def adaptive_cache_3D(T=np.float64, max_levels: int = 5) -> AdaptiveCache:
+def adaptive_cache_3D(T=np.float64, max_levels: int = 5, on_device: bool = False) -> AdaptiveCache:
     """adaptive_cache_3D(T; max_levels=5)   caches.jl:219-220"""
-    return _cache(_dt(T), 3, 0, max_levels)
+    return _cache(_dt(T), 3, 0, max_levels, on_device)
 
 
-def adaptive_cache_2D_cmpl(T=np.float64, max_levels: int = 8) -> AdaptiveCache:
+def adaptive_cache_2D_cmpl(T=np.float64, max_levels: int = 8, on_device: bool = False) -> AdaptiveCache:
     """Tensor-complement cache (extension for BASELINE config C; window t_w_max(T, 2))."""
-    return _cache(_dt(T), 2, 1, max_levels)
+    return _cache(_dt(T), 2, 1, max_levels, on_device)
+
+
+class DeviceTables:
+    """Fixed tanh-sinh grid generated on the device (fts_tables_fixed_create): `x, w, h` are a
+    download of it; `handle` goes to the *_dev launches."""
+
+    def __init__(self, T=np.float64, N: int = 2, D: int = 1):
+        dt = _dt(T)
+        self.dtype = dt
+        self.handle = C.c_void_p()
+        L.check(L.lib.fts_tables_fixed_create(_DT_CODE[dt], int(N), int(D), C.byref(self.handle)))
+        n = C.c_int()
+        h = np.zeros(1, dt)
+        L.check(L.lib.fts_tables_download(self.handle, C.byref(n), None, None, _ptr(h)))
+        self.x, self.w = np.zeros(n.value, dt), np.zeros(n.value, dt)
+        L.check(L.lib.fts_tables_download(self.handle, None, _ptr(self.x), _ptr(self.w), None))
+        self.h = h[0]
+
+    def __del__(self):
+        try:
+            L.lib.fts_tables_free(self.handle)
+        except Exception:
+            pass
 
 
 def _require_cache_levels(cache: AdaptiveCache, max_levels: int) -> AdaptiveCache:

@@ -206,6 +206,19 @@ int fts_cache_tensor_cmpl_upload(int dtype, int max_levels, const void* tm, cons
                                  const void* initial_w, const void* initial_c, const void* xs_flat,
                                  const void* ws_flat, const void* cs_flat, fts_cache* out);
 /* length(cache.xs) (caches.jl:25-29 depth guard) and D (0 for 1D caches) */
+/* ---- on-device generation ------------------------------------------------------
+ * The same tables as fts_tanhsinh / fts_cache*_generate (core.jl:126-185, 256-267;
+ * caches.jl:59-91, 148-188), computed by one thread per node straight into device memory: no host
+ * arrays, no upload.  Float32/Float64 use CUDA's libm, Double64 double-double series; values agree
+ * with the host generators to a few ulp (not bit for bit: different libm).
+ * fts_cache_create: D = 0 -> 1D cache (kind 0 regular, 1 complement); D = 2, 3 -> tensor cache;
+ * D = 2 with kind 1 -> the 2D complement table. */
+int fts_tables_fixed_create(int dtype, int N, int D, fts_tables* out);
+int fts_cache_create(int dtype, int D, int kind, int max_levels, fts_cache* out);
+/* Read a table back in the layout the *_upload calls take (any output pointer may be null). */
+int fts_tables_download(fts_tables t, int* n, void* x, void* w, void* h);
+int fts_cache_download(fts_cache c, void* tm, void* initial_x, void* initial_w, void* initial_c,
+                       void* xs_flat, void* ws_flat, void* cs_flat);
 int fts_cache_info(fts_cache c, int* dtype, int* D, int* kind, int* max_levels);
 int fts_cache_free(fts_cache c);
 

@@ -596,3 +596,51 @@ def test_config_e_double64(gpu, oracle):
     # Double64 quad of exp on [0,1] (runtests.jl:211-215)
     vd = gpu.quad(gpu.builtin("exp"), gpu.to_dd([0.0]), gpu.to_dd([1.0]), rtol=1e-15)
     assert abs(gpu.dd_to_mpf(vd)[0] - (mpmath.e - 1)) < mpmath.mpf("1e-15")
+
+
+# ------------------------------------------------------------------ on-device tables ----------
+def test_on_device_table_generation(gpu):
+    """fts_cache_create / fts_tables_fixed_create: tables computed by kernels in HBM
+    against the host generators (which test_host_logic pins bitwise on the oracle).  Different
+    libm -> agreement to a few ulp, amplified in the tail weights by the argument of cosh
+    (|u| <= 700: 1 ulp of u moves w by 700 ulp); the integrals agree to the parity tolerances."""
+    import mpmath
+    eps = {np.dtype(np.float32): 2.0 ** -23, np.dtype(np.float64): 2.0 ** -52}
+    for T in (np.float32, np.float64):
+        dt, e = np.dtype(T), eps[np.dtype(T)]
+        for ctor, kw in ((gpu.adaptive_cache_1D, dict(max_levels=10)), (gpu.adaptive_cache_1D, dict(max_levels=10, complement=True)),
+                         (gpu.adaptive_cache_2D, dict(max_levels=6)), (gpu.adaptive_cache_3D, dict(max_levels=4)),
+                         (gpu.adaptive_cache_2D_cmpl, dict(max_levels=5))):
+            host, dev = ctor(T, **kw), ctor(T, on_device=True, **kw)
+            assert dev.tm == host.tm and dev._xs.shape == host._xs.shape
+            assert np.max(np.abs(dev._xs - host._xs)) <= 4 * e and np.max(np.abs(dev.initial_x - host.initial_x)) <= 4 * e
+            big = host._ws > np.finfo(dt).tiny * 1e6
+            assert np.max(np.abs(dev._ws[big] - host._ws[big]) / host._ws[big]) <= 2000 * e
+            assert np.max(np.abs(dev._ws[~big] - host._ws[~big]), initial=0.0) <= np.finfo(dt).tiny * 1e7
+            if host.kind == 1:
+                nz = host._cs > np.finfo(dt).tiny * 1e6
+                assert np.max(np.abs(dev._cs[nz] - host._cs[nz]) / host._cs[nz], initial=0.0) <= 2000 * e
+                assert np.max(np.abs(dev.initial_c - host.initial_c) / host.initial_c) <= 2000 * e
+        x, w, h = gpu.tanhsinh(T, 80)
+        t = gpu.DeviceTables(T, 80)
+        assert t.h == h and np.max(np.abs(t.x - x)) <= 4 * e and np.max(np.abs(t.w - w) / w) <= 2000 * e
+    # integrals through device-generated caches
+    a = _alpha(4096)
+    rh = gpu.quad(gpu.builtin("gauss"), -1.0, 1.0, rtol=1e-10, cache=gpu.adaptive_cache_1D(np.float64, max_levels=16), params=a, full_output=True)
+    rd = gpu.quad(gpu.builtin("gauss"), -1.0, 1.0, rtol=1e-10, cache=gpu.adaptive_cache_1D(np.float64, max_levels=16, on_device=True), params=a,
+                  full_output=True)
+    same = rh.levels == rd.levels
+    assert same.mean() > 0.99 and rel(rd.value[same], rh.value[same]).max() <= RTOL64
+    v3 = gpu.adaptive_integrate_3D(np.float64, gpu.builtin("exp_3d"), [-1.0] * 3, [1.0] * 3, rtol=1e-9, max_levels=5,
+                                   cache=gpu.adaptive_cache_3D(np.float64, max_levels=5, on_device=True))
+    assert rel(v3, (math.e - 1 / math.e) ** 3) <= 1e-12
+    # Double64: device double-double series against the host's __float128 tables
+    mpmath.mp.dps = 50
+    host, dev = gpu.adaptive_cache_1D(gpu.Double64, max_levels=9, complement=True), gpu.adaptive_cache_1D(gpu.Double64, max_levels=9, complement=True, on_device=True)
+    for name, tol in (("_xs", "1e-31"), ("_ws", "2e-28"), ("_cs", "2e-28")):
+        hv, dv = gpu.dd_to_mpf(getattr(host, name)), gpu.dd_to_mpf(getattr(dev, name))
+        worst = max((abs(d - h_) / abs(h_) if (name != "_xs" and abs(h_) > mpmath.mpf("1e-290")) else abs(d - h_)) for d, h_ in zip(dv, hv))
+        assert worst <= mpmath.mpf(tol), (name, worst)
+    vd = gpu.quad_cmpl(gpu.builtin("c_exp_inv_bmx"), gpu.to_dd([0.0]), gpu.to_dd([1.0]), rtol="1e-28", max_levels=12,
+                       cache=gpu.adaptive_cache_1D(gpu.Double64, max_levels=12, complement=True, on_device=True))
+    assert abs(gpu.dd_to_mpf(vd)[0] - (mpmath.exp(-1) - mpmath.e1(1))) < mpmath.mpf("1e-28")
