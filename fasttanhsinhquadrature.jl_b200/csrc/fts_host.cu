@@ -970,7 +970,6 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     const void *fn_cta = nullptr, *fn_grid = nullptr;
     size_t smem_cta = 0;
     const Style st = adaptive_style(c, f, order, max_levels, batch, &fn_cta, &fn_grid, &smem_cta);
-    (void)cmpl;
     if (st == STYLE_GRID)
         return run_adaptive_grid<T>(fn_grid, c, f, options, (const T*)low, (const T*)up, bstride, (const T*)params, pstride, load_elem<T>(rtol),
                                     load_elem<T>(atol), max_levels, batch, (T*)out_value, (T*)out_err, out_levels, out_flags, s);
@@ -984,6 +983,28 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     a.value = (T*)out_value; a.err = (T*)out_err; a.levels = out_levels; a.flags = out_flags;
     if (st == STYLE_CTA) {
         if (batch > 0x7fffffffLL) return set_error(FTS_ERR_INVALID_ARGUMENT, "batch too large for one launch");
+        // 2D batches large enough to fill the GPU with warps: one WARP per integral up to level
+        // `lw` (no CTA barriers; shallow integrals such as config C stop at level 4), the rest is
+        // queued and finished by whole CTAs in a second launch of the same kernel
+        static const int kWarpLevels = [] { const char* e = getenv("FTS_B200_WARP2D_LEVELS"); const int v = e ? atoi(e) : 5; return v < 0 ? -1 : (v > 7 ? 7 : v); }();
+        if (dim == 2 && kWarpLevels >= 0 && batch >= 8LL * g_prop.multiProcessorCount) {
+            const int lw = max_levels < kWarpLevels ? max_levels : kWarpLevels;
+            const int warps = fts::CTA_THREADS / 32;
+            const size_t smem_w = (size_t)warps * (cmpl ? 9 : 5) * ((size_t)2 << lw) * sizeof(T);
+            int* queue = nullptr;
+            if (int rc = tail_queue_for(s, (size_t)batch, &queue)) return rc;
+            a.tail_count = queue;
+            a.ticket = (unsigned int*)(queue + 1);
+            a.tail_idx = queue + 2;
+            a.group = 32;
+            a.level = lw;
+            if (int rc = launch_raw(fn_cta, (unsigned)((batch + warps - 1) / warps), fts::CTA_THREADS, smem_w, &a, s)) return rc;
+            if (lw == max_levels) return FTS_OK;  // nothing can be queued
+            a.group = 0;
+            a.level = 0;
+            const long long cap = (long long)g_prop.multiProcessorCount * 8;
+            return launch_raw(fn_cta, (unsigned)(batch < cap ? batch : cap), fts::CTA_THREADS, smem_cta, &a, s);
+        }
         return launch_raw(fn_cta, (unsigned)batch, fts::CTA_THREADS, smem_cta, &a, s);
     }
     const int fast = order == FTS_ORDER_FAST ? 1 : 0;

@@ -69,6 +69,9 @@ template <class T> struct Args {
     int tail_level;       // < 0: disabled
     int* tail_count;
     int* tail_idx;
+    // launch shape of the grouped 2D adaptive kernel (k_adaptive2d_cta): 0 = CTA per integral,
+    // 32 = warp per integral with `level` as the deepest level a warp handles
+    int group;
     // fused exchange over NVLink peer memory (k_level_grid epilogue): the last CTA stores this
     // rank's (s, c) and then the epoch flag straight into every rank's mailbox
     double* peer_mail[FTS_MAX_RANKS];  // mailbox of rank r mapped into this process (own one included); null: no exchange

@@ -185,10 +185,11 @@ template <class T, bool CMPL> __device__ __forceinline__ void sm2_carve(Sm2<T>& 
 // stage one level; `x,w,c` given as strided element pointers so that Node / NodeC / initial
 // tuples all fit (stride in elements)
 template <class T, bool CMPL>
-__device__ __forceinline__ void sm2_stage(Sm2<T>& s, const T* x, const T* w, const T* c, int stride, int n)
+__device__ __forceinline__ void sm2_stage(Sm2<T>& s, const T* x, const T* w, const T* c, int stride, int n, int tid = threadIdx.x,
+                                          int nthr = blockDim.x)
 {
     const T one = num<T>::one();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += nthr) {
         const T xi = x[(size_t)i * stride], wi = w[(size_t)i * stride];
         s.xp[i] = fm::fma(s.dx, xi, s.x0);
         s.xm[i] = fm::fma(-s.dx, xi, s.x0);
@@ -273,22 +274,34 @@ __device__ __forceinline__ T level_sum_2d(const Sm2<T>& s, const T* p, int n, in
 
 extern __shared__ __align__(16) unsigned char fts_dyn_smem[];
 
-// adaptive_integrate_2D_avx (+ tensor-complement extension)   adaptive.jl:242-333
-template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive2d_cta(const Args<T> a)
+// A "group" of G threads owns one integral: the whole CTA (G = CTA_THREADS) or one warp (G = 32).
+template <int G> __device__ __forceinline__ void group_sync()
 {
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
+    if constexpr (G == 32) __syncwarp();
+    else __syncthreads();
+}
+template <class T, int G> __device__ __forceinline__ Comp<T> group_reduce(Comp<T> v, T* red)  // valid in the group's thread 0
+{
+    if constexpr (G == 32) return warp_reduce(v);
+    else return block_reduce(v, red);
+}
+
+// adaptive_integrate_2D_avx (+ tensor-complement extension)   adaptive.jl:242-333
+// One integral by a group of G threads (`gtid` = index in the group).  `level_cap` < max_levels:
+// an integral that has not converged after level_cap is queued (a.tail_idx) for a second pass by
+// whole CTAs instead of going deeper here (the group's shared-memory slice holds 2^(level_cap+1)
+// nodes per array).
+template <class T, class F, int G>
+__device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, int gtid, T* smem, int ncap, int level_cap, T* red, int* s_done)
+{
     constexpr bool CMPL = is_cmpl2d<F>::value;
-    __shared__ T red[64];
-    __shared__ int s_done;
-    const long long b = blockIdx.x;
-    const int tid = threadIdx.x;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, b);
     T lo[2], hi[2];
     bool neg;
     int flags;
     if (!load_box<2>(a, b, lo, hi, neg, flags)) {
-        if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        if (gtid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
         return;
     }
     const T half = num<T>::half();
@@ -296,35 +309,40 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
     s.dx = half * (hi[0] - lo[0]); s.x0 = half * (hi[0] + lo[0]);
     s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
     s.w0 = num<T>::half_pi();
-    const int nmax = a.max_levels > 0 ? (2 << a.max_levels) : 2;
-    sm2_carve<T, CMPL>(s, reinterpret_cast<T*>(fts_dyn_smem), nmax);
+    sm2_carve<T, CMPL>(s, smem, ncap);
     T h = a.tm * half;
     // level 0: base grid {h, 2h}, all cells new (adaptive.jl:264-272)
-    sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2);
-    __syncthreads();
-    T acc = level_sum_2d<T, F, CMPL>(s, p, 2, 1, true, tid, blockDim.x);
-    if (tid == 0) {
+    sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2, gtid, G);
+    group_sync<G>();
+    T acc = level_sum_2d<T, F, CMPL>(s, p, 2, 1, true, gtid, G);
+    if (gtid == 0) {
         if constexpr (CMPL) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.dx, s.dx, s.dy, s.dy, p);
         else acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
     }
-    Comp<T> s_total = block_reduce(comp_of(acc), red);
+    Comp<T> s_total = group_reduce<T, G>(comp_of(acc), red);
     T old_res = s.dx * s.dy * (h * h) * s_total.value();
     T err = num<T>::zero();
     int level_used = 0;
     for (int level = 1; level <= a.max_levels; ++level) {
+        if (level > level_cap) {  // too deep for this group's shared-memory slice: whole-CTA pass
+            if (gtid == 0) a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
+            return;
+        }
         h = h * half;
         const int n = 2 << level;
+        group_sync<G>();  // every thread is done with the previous level's coordinates
         if constexpr (CMPL) {
             const NodeC<T>* lv = a.nodes_c + (n - 4);
-            sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n);
+            sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n, gtid, G);
         } else {
             const Node<T>* lv = a.nodes + (n - 4);
-            sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n);
+            sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n, gtid, G);
         }
-        __syncthreads();
-        acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, false, tid, blockDim.x);
-        const Comp<T> lv_sum = block_reduce(comp_of(acc), red);
-        if (tid == 0) {
+        group_sync<G>();
+        acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, false, gtid, G);
+        const Comp<T> lv_sum = group_reduce<T, G>(comp_of(acc), red);
+        int done = 0;
+        if (gtid == 0) {
             s_total.merge(lv_sum);
             const T new_res = s.dx * s.dy * (h * h) * s_total.value();
             err = fm::abs(new_res - old_res);
@@ -332,14 +350,59 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
             level_used = level;
             const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
             if (conv) flags |= FLAG_CONVERGED;
-            s_done = conv ? 1 : 0;
+            done = conv ? 1 : 0;
         }
-        __syncthreads();
-        if (s_done) break;
+        if constexpr (G == 32) {
+            done = __shfl_sync(0xffffffffu, done, 0);
+        } else {
+            if (gtid == 0) *s_done = done;
+            __syncthreads();
+            done = *s_done;
+        }
+        if (done) break;
     }
-    if (tid == 0) {
+    if (gtid == 0) {
         if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
         store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
+// Launch shapes (Args::group): 0 = one CTA per integral (blockIdx = integral, or — with a queue in
+// a.tail_idx — the CTAs walk the queued integrals); 32 = one WARP per integral, levels <= a.level
+// (shallow integrals: 4 225 evaluations at level 4 keep 32 lanes busy without any CTA barrier;
+// config C 68 -> about 20 us), deeper ones are queued for a second launch in shape 0.
+template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive2d_cta(const Args<T> a)
+{
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    __shared__ T red[64];
+    __shared__ int s_done;
+    T* smem = reinterpret_cast<T*>(fts_dyn_smem);
+    if (a.group == 32) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const long long b = (long long)blockIdx.x * (CTA_THREADS / 32) + warp;
+        if (b >= a.batch) return;
+        const int ncap = 2 << a.level;
+        adaptive2d_group<T, F, 32>(a, b, lane, smem + (size_t)warp * sm2_elems<T, CMPL>(ncap), ncap, a.level, nullptr, nullptr);
+        return;
+    }
+    const int nmax = a.max_levels > 0 ? (2 << a.max_levels) : 2;
+    if (a.tail_idx == nullptr) {
+        adaptive2d_group<T, F, CTA_THREADS>(a, blockIdx.x, threadIdx.x, smem, nmax, a.max_levels, red, &s_done);
+        return;
+    }
+    const int count = *a.tail_count;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        adaptive2d_group<T, F, CTA_THREADS>(a, a.tail_idx[q], threadIdx.x, smem, nmax, a.max_levels, red, &s_done);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {  // the last CTA to leave re-arms the queue (see k_adaptive1d_tail)
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *a.tail_count = 0;
+            *a.ticket = 0u;
+        }
     }
 }
 

@@ -412,6 +412,49 @@ def test_adaptive_2d_orders(gpu, oracle):
     assert abs(gpu.quad_split(gpu.builtin("x2py2"), [0.0, 0.0], [-1.0, -1.0], [1.0, 1.0], rtol=1e-9, max_levels=8) - 8 / 3) < 1e-9        # dispatch.jl:1-9
 
 
+def test_adaptive_2d_warp_per_integral_and_queue(gpu, oracle):
+    """2D batches of >= 8 x SMs integrals in the cooperative order run one WARP per integral up to
+    level 5; integrals that need more are queued and finished by whole CTAs.  Mixed batch: smooth
+    boxes (stop at level 3-5), endpoint-singular ones (levels 6-8), zero-width and flipped boxes."""
+    oc = oracle.cache_tensor("f64", 2, 8)
+    cache = gpu.adaptive_cache_2D(np.float64, max_levels=8)
+    n = 3000
+    rng = np.random.default_rng(11)
+    low = np.stack([-1 - rng.random(n), -1 - rng.random(n)], axis=1)
+    up = np.stack([1 + rng.random(n), 0.5 + rng.random(n)], axis=1)
+    low[5], up[5] = (0.25, -1.0), (0.25, 2.0)        # zero width -> 0
+    low[6], up[6] = (1.0, -1.0), (0.0, 2.0)          # flipped x -> negated
+    r = gpu.quad(gpu.builtin("exp_2d"), low, up, rtol=1e-9, max_levels=8, cache=cache, order="fast", full_output=True)
+    exact = (np.exp(up[:, 0]) - np.exp(low[:, 0])) * (np.exp(up[:, 1]) - np.exp(low[:, 1]))
+    assert r.converged.all() and r.value[5] == 0.0 and r.levels.max() <= 5
+    assert rel(np.delete(r.value, 5), np.delete(exact, 5)).max() < 1e-9
+    for i in (0, 6, 7, 1499, 2999):
+        lo_i, up_i = (low[i], up[i]) if i != 6 else (np.array([0.0, -1.0]), np.array([1.0, 2.0]))
+        refx = oracle.adaptive_nd("f64x", 2, F["F2_EXP"], None, lo_i, up_i, 1e-9, 0.0, 8, oc)
+        assert r.levels[i] == refx.level and rel(abs(r.value[i]), refx.value) <= RTOL64
+    # an interior singularity (1/sqrt|xy| on [-1,2]^2) never meets the tolerance: every integral
+    # outgrows the warp pass (level 5), is queued, and runs to max_levels in the whole-CTA pass
+    sub_lo, sub_up = np.full((1500, 2), -1.0), np.full((1500, 2), 2.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rs = gpu.adaptive_integrate_2D_avx(np.float64, gpu.builtin("invsqrtabs_2d"), sub_lo, sub_up, rtol=1e-12, max_levels=7, cache=cache,
+                                           full_output=True)
+        refx = oracle.adaptive_nd("f64x", 2, F["F2_INVSQRTABS"], None, sub_lo[0], sub_up[0], 1e-12, 0.0, 7, oc)
+        assert refx.level == 7 and (rs.levels == 7).all() and not rs.converged.any() and rel(rs.value, refx.value).max() <= 1e-13
+        assert np.unique(rs.value).size == 1          # same box -> same bits, whichever CTA finished it
+        # and again: the queue re-arms itself between launches
+        rs2 = gpu.adaptive_integrate_2D_avx(np.float64, gpu.builtin("invsqrtabs_2d"), sub_lo, sub_up, rtol=1e-12, max_levels=7, cache=cache,
+                                            full_output=True)
+    assert np.array_equal(rs.value, rs2.value) and np.array_equal(rs.levels, rs2.levels)
+    # boxes of very different sizes in one launch
+    mix_lo, mix_up = low.copy(), up.copy()
+    mix_lo[1::3], mix_up[1::3] = -1e-3, 1e-3
+    rm = gpu.quad(gpu.builtin("exp_2d"), mix_lo, mix_up, rtol=1e-9, max_levels=8, cache=cache, order="fast", full_output=True)
+    ex = (np.exp(mix_up[:, 0]) - np.exp(mix_lo[:, 0])) * (np.exp(mix_up[:, 1]) - np.exp(mix_lo[:, 1]))
+    keep = np.arange(n) != 5
+    assert rm.converged.all() and rel(rm.value[keep], ex[keep]).max() < 1e-9
+
+
 def test_adaptive_3d_orders(gpu, oracle):
     oc = oracle.cache_tensor("f64", 3, 6)
     cache = gpu.adaptive_cache_3D(np.float64, max_levels=6)

@@ -130,6 +130,44 @@ def case_c(reps):
              fp64_frac_nominal=(evals / t * 14.5 / 1e12 / FP64_PEAK) if T == np.float64 else None)
 
 
+def case_cdev(reps):
+    """config C with inputs resident in HBM: kernel-only time (CUDA events) of the cooperative 2D path"""
+    import torch
+    from fts_b200 import api
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    n = 4096
+    low = np.stack([-3 + 2 * rng.random(n), -3 + 2 * rng.random(n)], axis=1)
+    up = np.stack([1 + 2 * rng.random(n), 1 + 2 * rng.random(n)], axis=1)
+    exact = 4 * np.sqrt((up[:, 0] - low[:, 0]) * (up[:, 1] - low[:, 1]))
+    f = fts.builtin("c2_invsqrt_bmx_ymc")
+    stream = torch.cuda.current_stream().cuda_stream
+    for T, tt, rtol, ml in ((np.float64, torch.float64, 1e-10, 8), (np.float32, torch.float32, 1e-5, 6)):
+        cache = fts.adaptive_cache_2D_cmpl(T, max_levels=ml)
+        lo, hi = torch.from_numpy(low.astype(T)).to(dev), torch.from_numpy(up.astype(T)).to(dev)
+        val = torch.empty(n, dtype=tt, device=dev)
+        lev = torch.empty(n, dtype=torch.int32, device=dev)
+        ts = []
+        for it in range(reps + 3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            api.adaptive_batch_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), bounds_stride=2, params=0, params_stride=0, rtol=rtol, atol=0.0,
+                                   max_levels=ml, batch=n, value=val.data_ptr(), levels=lev.data_ptr(), stream=stream, order="fast",
+                                   options=1)  # FTS_OPT_QUAD_EDGE_RULES
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(e0.elapsed_time(e1))
+        t = min(ts) * 1e-3
+        levels = lev.cpu().numpy()
+        evals = int(evals_for_level(2, levels).sum())
+        emit(case="C-device", dtype=np.dtype(T).name, batch=n, ms=t * 1e3, ms_median=float(np.median(ts)), integrals_per_s=n / t,
+             gevals_per_s=evals / t / 1e9, levels=np.bincount(levels).tolist(),
+             max_rel_err_vs_exact=float(np.max(np.abs(val.cpu().numpy() - exact) / exact)),
+             fp64_frac_nominal=(evals / t * 14.5 / 1e12 / FP64_PEAK) if T == np.float64 else None,
+             warp2d_levels=os.environ.get("FTS_B200_WARP2D_LEVELS", "default(5)"))
+
+
 def case_d(reps):
     """config D on ONE GPU: a single adaptive 3D integral of exp(x+y+z), forced depth; flop/eval 32.1"""
     f = fts.builtin("exp_3d")
@@ -217,7 +255,7 @@ def main():
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
     emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
     for c in args.cases.split(","):
-        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
+        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "Cdev": case_cdev, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
 
 
 if __name__ == "__main__":
