@@ -32,15 +32,29 @@ def shard_range(batch: int, rank: int, world: int) -> tuple:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def shard_indices(batch: int, rank: int, world: int, layout: str = "contiguous"):
+    """Items of `rank`: a contiguous slice, or — layout="cyclic" — every world-th item starting at
+    `rank`.  Cyclic dealing equalises the COST per rank when the refinement depth varies smoothly
+    along the batch (a sorted parameter sweep: SURVEY 8e "cost-aware" partitioning) at the price of
+    strided host access."""
+    if layout == "cyclic":
+        return slice(rank, batch, world)
+    if layout != "contiguous":
+        raise ValueError("layout must be 'contiguous' or 'cyclic'")
+    start, stop = shard_range(batch, rank, world)
+    return slice(start, stop)
+
+
 def _dist():
     import torch.distributed as dist
     return dist
 
 
-def quad_sharded(f, low, up, *, params=None, gather: bool = True, group=None, **kw):
-    """`quad` over a batch sharded across the ranks of `group` (contiguous slices, no data-path
-    collective).  Returns the full result vector on every rank when gather=True, else the local
-    slice and its (start, stop)."""
+def quad_sharded(f, low, up, *, params=None, gather: bool = True, group=None, layout: str = "contiguous", **kw):
+    """`quad` over a batch sharded across the ranks of `group` (no data-path collective).
+    layout="contiguous": rank r owns a contiguous slice; "cyclic": items r, r+world, ... (equal
+    cost per rank for sorted sweeps).  Returns the full result vector, in the caller's order, on
+    every rank when gather=True, else the local results and their slice (start, stop[, step])."""
     import torch
     dist = _dist()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -50,21 +64,27 @@ def quad_sharded(f, low, up, *, params=None, gather: bool = True, group=None, **
     batched_bounds = low_a.ndim == (1 if dim == 1 else 2)
     p = None if params is None else np.asarray(params)
     n = low_a.shape[0] if batched_bounds else (p.shape[0] if p is not None and p.ndim >= 1 else 1)
-    start, stop = shard_range(n, rank, world)
-    lo_l = low_a[start:stop] if batched_bounds else low
-    up_l = up_a[start:stop] if batched_bounds else up
-    p_l = p[start:stop] if (p is not None and p.ndim >= 1 and p.shape[0] == n) else params
-    local = np.atleast_1d(api.quad(f, lo_l, up_l, params=p_l, **kw)) if stop > start else np.zeros(0)
+    mine = shard_indices(n, rank, world, layout)
+    nloc = len(range(*mine.indices(n)))
+    lo_l = np.ascontiguousarray(low_a[mine]) if batched_bounds else low
+    up_l = np.ascontiguousarray(up_a[mine]) if batched_bounds else up
+    p_l = np.ascontiguousarray(p[mine]) if (p is not None and p.ndim >= 1 and p.shape[0] == n) else params
+    local = np.atleast_1d(api.quad(f, lo_l, up_l, params=p_l, **kw)) if nloc > 0 else np.zeros(0)
     if not gather or world == 1:
-        return (local, (start, stop)) if not gather else local
-    sizes = [shard_range(n, r, world) for r in range(world)]
-    width = max(b - a for a, b in sizes)
+        where = (mine.start, mine.stop) if layout == "contiguous" else (mine.start, mine.stop, mine.step)
+        return (local, where) if not gather else local
+    parts = [shard_indices(n, r, world, layout) for r in range(world)]
+    sizes = [len(range(*q.indices(n))) for q in parts]
+    width = max(sizes)
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     buf = torch.zeros(width, dtype=torch.float64, device=dev)
     buf[: local.shape[0]] = torch.from_numpy(np.asarray(local, np.float64))
     out = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
-    return np.concatenate([o[: b - a].cpu().numpy() for o, (a, b) in zip(out, sizes)])
+    full = np.empty(n, np.float64)
+    for o, q, m in zip(out, parts, sizes):
+        full[q] = o[:m].cpu().numpy()
+    return full
 
 
 def run_sharded_levels(max_levels: int, rank: int, world: int, level_fn: Callable, step_fn: Callable, all_gather: Callable,

@@ -26,7 +26,17 @@ def _free_port():
 
 
 def test_shard_range_partitions(fts):
-    from fts_b200.distributed import shard_range
+    from fts_b200.distributed import shard_range, shard_indices
+    for n in (0, 1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            for layout in ("contiguous", "cyclic"):
+                got = np.concatenate([np.arange(n)[shard_indices(n, r, world, layout)] for r in range(world)])
+                assert np.array_equal(np.sort(got), np.arange(n))
+    # a linear cost ramp (a sorted sweep): cyclic dealing balances it, contiguous slices do not
+    cost = np.linspace(1.0, 3.0, 1 << 12)
+    cyc = [cost[shard_indices(cost.size, r, 8, "cyclic")].sum() for r in range(8)]
+    con = [cost[shard_indices(cost.size, r, 8, "contiguous")].sum() for r in range(8)]
+    assert max(cyc) / min(cyc) < 1.002 and max(con) / min(con) > 2.0
     for n in (0, 1, 7, 8, 1 << 20, 65537):
         for world in (1, 2, 3, 8):
             parts = [shard_range(n, r, world) for r in range(world)]
@@ -96,6 +106,10 @@ def _worker(rank, world, port, out):
         f = api.builtin("gauss")
         full = distributed.quad_sharded(f, lows, np.ones(n), params=alpha)
         local, (a, b) = distributed.quad_sharded(f, lows, np.ones(n), params=alpha, gather=False)
+        full_cyc = distributed.quad_sharded(f, lows, np.ones(n), params=alpha, layout="cyclic")
+        loc_cyc, where_cyc = distributed.quad_sharded(f, lows, np.ones(n), params=alpha, gather=False, layout="cyclic")
+        assert where_cyc == (rank, n, world) and np.array_equal(loc_cyc, (alpha[:, 0] * 2.0 + lows)[rank::world])
+        assert np.array_equal(full_cyc, alpha[:, 0] * 2.0 + lows)
     finally:
         api.quad = real_quad
     ref = orc.adaptive_nd("f64", 3, F["F3_EXP"], None, low, up, rtol, atol, L, oc)
