@@ -723,7 +723,7 @@ static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, 
 {
     const int dim = kind_dim(f->kind);
     const void* fn_cta = t->dtype == FTS_DD64 ? nullptr : integrand_kernel(f, t->dtype, KID_FIXED_CTA, 1);
-    const size_t smem = dim == 1 ? 0 : (size_t)(dim == 2 ? 5 : 7) * t->n * sizeof(T);
+    const size_t smem = dim == 1 ? 0 : (size_t)(dim == 2 ? 5 : fts::SM3_ARRAYS) * t->n * sizeof(T);
     const bool cta_ok = fn_cta && smem <= dyn_smem_limit();
     Style st = pick_style(order, dim, batch, 0, cta_ok, false);
     fts::Args<T> a;
@@ -834,7 +834,7 @@ __global__ void k_state_to_result(const T* state, const T* low, const T* up, int
 static size_t grid_level_smem(int dim, bool cmpl, int level, size_t es)
 {
     const size_t n = level == 0 ? 2 : ((size_t)2 << level);
-    return (dim == 3 ? 7 : (cmpl ? 9 : 5)) * n * es;
+    return (dim == 3 ? fts::SM3_ARRAYS : (cmpl ? 9 : 5)) * n * es;
 }
 
 static unsigned grid_level_blocks(int dim, int level, int nranks)
@@ -949,7 +949,7 @@ static Style adaptive_style(fts_cache c, fts_integrand f, int order, int max_lev
     const void* fn_cta = is_dd ? nullptr : integrand_kernel(f, c->dtype, KID_ADAPT_CTA, 1);
     const void* fn_grid = (is_dd || dim == 1) ? nullptr : integrand_kernel(f, c->dtype, KID_LEVEL_GRID, 1);
     const size_t nmax = max_levels > 0 ? ((size_t)2 << max_levels) : 2;
-    const size_t smem_cta = dim == 1 ? 0 : (dim == 3 ? 7 : (cmpl ? 9 : 5)) * nmax * es;
+    const size_t smem_cta = dim == 1 ? 0 : (dim == 3 ? fts::SM3_ARRAYS : (cmpl ? 9 : 5)) * nmax * es;
     const bool cta_ok = fn_cta && smem_cta <= dyn_smem_limit();
     const bool grid_ok = fn_grid && grid_level_smem(dim, cmpl, max_levels, es) <= dyn_smem_limit();
     if (fn_cta_out) *fn_cta_out = fn_cta;

@@ -434,12 +434,19 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fix
 // ------------------------------------------------------------------------------------ 3D -----
 template <class T> struct Sm3 {
     T *xp, *xm, *yp, *ym, *zp, *zm, *w;
+    // z coordinates and weights once more, permuted k -> (k mod 4)(n/4) + k/4: the lanes of a warp
+    // walk runs of 4 consecutive k (cells3_run), lane m at k = 4m + c, and read element c(n/4) + m —
+    // consecutive words, no bank conflicts (stride-4 reads of the natural layout are 4-way)
+    T *zpq, *zmq, *wq;
     T dx, x0, dy, y0, dz, z0, w0;
 };
+constexpr int SM3_ARRAYS = 10;
+__device__ __forceinline__ int sm3_q(int k, int n) { return (k & 3) * (n >> 2) + (k >> 2); }
 
 template <class T> __device__ __forceinline__ void sm3_carve(Sm3<T>& s, T* base, int n)
 {
     s.xp = base; s.xm = base + n; s.yp = base + 2 * n; s.ym = base + 3 * n; s.zp = base + 4 * n; s.zm = base + 5 * n; s.w = base + 6 * n;
+    s.zpq = base + 7 * n; s.zmq = base + 8 * n; s.wq = base + 9 * n;
 }
 
 // the reference's coordinate hoist (adaptive.jl:570-580), into shared memory
@@ -454,6 +461,10 @@ template <class T> __device__ __forceinline__ void sm3_stage(Sm3<T>& s, const T*
         s.zp[i] = fm::fma(s.dz, xi, s.z0);
         s.zm[i] = fm::fma(-s.dz, xi, s.z0);
         s.w[i] = w[(size_t)i * stride];
+        const int q = sm3_q(i, n);
+        s.zpq[q] = s.zp[i];
+        s.zmq[q] = s.zm[i];
+        s.wq[q] = s.w[i];
     }
 }
 
@@ -475,6 +486,35 @@ template <class T, class F> __device__ __forceinline__ T cell3(const Sm3<T>& s, 
             ((FTS_FE(xp, yp, zm) + FTS_FE(xm, yp, zm)) + (FTS_FE(xp, ym, zm) + FTS_FE(xm, ym, zm)));
     }
     return (s.w[i] * s.w[j] * s.w[k]) * f;
+}
+// CH cells along k (k0, k0+kstep, ...) that share (i, j): the x/y coordinates, w_i*w_j and whatever
+// the integrand computes from x and y alone (log(1-x)log(1-y)...) are formed once per run instead
+// of once per cell, and the flat-index decode is paid once per CH cells.
+template <class T, class F, int CH> __device__ __forceinline__ T cells3_run(const Sm3<T>& s, const T* p, int n, int i, int j, int k0, int kstep)
+{
+    const T xp = s.xp[i], xm = s.xm[i], yp = s.yp[j], ym = s.ym[j];
+    T acc = num<T>::zero();
+    // interleaved-batch integrands already keep 8 chains in flight per cell: unrolling the run as
+    // well costs 30+ registers (156 -> 1 CTA/SM); everyone else is unrolled so that common
+    // sub-expressions of the CH cells merge
+    constexpr int UNROLL = 1;
+#pragma unroll UNROLL
+    for (int c = 0; c < CH; ++c) {
+        const int q = sm3_q(k0 + c * kstep, n);
+        const T zp = s.zpq[q], zm = s.zmq[q];
+        T f;
+        if constexpr (HasEvalN<F>::value) {
+            const T xs[8] = {xp, xm, xp, xm, xp, xm, xp, xm}, ys[8] = {yp, yp, ym, ym, yp, yp, ym, ym}, zs[8] = {zp, zp, zp, zp, zm, zm, zm, zm};
+            T v[8];
+            eval3d_n<T, F, true, 8, UsesExpTab<T, F>::value ? EXP_SMEM : 0>(xs, ys, zs, p, v);
+            f = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        } else {
+            f = ((FTS_FE(xp, yp, zp) + FTS_FE(xm, yp, zp)) + (FTS_FE(xp, ym, zp) + FTS_FE(xm, ym, zp))) +
+                ((FTS_FE(xp, yp, zm) + FTS_FE(xm, yp, zm)) + (FTS_FE(xp, ym, zm) + FTS_FE(xm, ym, zm)));
+        }
+        acc = fm::fma(s.wq[q], f, acc);
+    }
+    return (s.w[i] * s.w[j]) * acc;
 }
 template <class T, class F> __device__ __forceinline__ T plane3(const Sm3<T>& s, const T* p, int i, int j)
 {
@@ -531,7 +571,34 @@ __device__ __forceinline__ T level_sum_3d(const Sm3<T>& s, const T* p, int n, in
         const long long n3 = 1LL << (3 * l2);
         const long long nA = n3 >> 1, nB = n3 >> 2, nC = n3 >> 3;
         const long long ncell = nA + nB + nC;
-        for (long long t = start; t < ncell; t += stride) {
+        // Runs of CH cells along k when every thread gets several of them (rows hold n, or n/2 in
+        // class C, cells and every class size is a multiple of CH for n >= 2 CH).
+        constexpr int CH = 4;
+        const bool runs = n >= 2 * CH && ncell / CH >= 4 * stride;
+        for (long long u4 = start; runs && u4 < ncell / CH; u4 += stride) {
+            const long long t = u4 * CH;
+            int i, j, k, kstep = 1;
+            if (t < nA) {
+                i = (int)(t >> (2 * l2)) << 1;
+                j = (int)(t >> l2) & (n - 1);
+                k = (int)t & (n - 1);
+            } else if (t < nA + nB) {
+                const long long u = t - nA;
+                i = ((int)(u >> (2 * l2 - 1)) << 1) | 1;
+                const int r = (int)(u & ((1LL << (2 * l2 - 1)) - 1));
+                j = (r >> l2) << 1;
+                k = r & (n - 1);
+            } else {
+                const long long u = t - nA - nB;
+                i = ((int)(u >> (2 * l2 - 2)) << 1) | 1;
+                const int r = (int)(u & ((1LL << (2 * l2 - 2)) - 1));
+                j = ((r >> (l2 - 1)) << 1) | 1;
+                k = (r & ((n >> 1) - 1)) << 1;
+                kstep = 2;
+            }
+            acc = acc + cells3_run<T, F, CH>(s, p, n, i, j, k, kstep);
+        }
+        for (long long t = start; !runs && t < ncell; t += stride) {
             int i, j, k;
             if (t < nA) {
                 i = (int)(t >> (2 * l2)) << 1;
