@@ -670,16 +670,20 @@ static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, voi
     return FTS_OK;
 }
 
-// threads per CTA of the thread-per-integral kernels (FTS_B200_TPI_BLOCK overrides the 1D value
-// for experiments; must not exceed the kernels' __launch_bounds__)
-static int tpi_block(int dim)
+// threads per CTA of the 1D thread-per-integral kernels: 128 (8 192 CTAs for 2^20 Float64
+// integrals: shorter tail than 256, 0.286 vs 0.290 ms on config B); Double64 prefers 256 (config E
+// 0.378 vs 0.394 ms); smaller CTAs for small batches were measured and do not help.
+// FTS_B200_TPI_BLOCK pins the value (experiments; must not exceed the kernels' __launch_bounds__).
+static int tpi_block(int dim, int dtype)
 {
-    static const int env1d = [] {
+    static const int pinned = [] {
         const char* e = getenv("FTS_B200_TPI_BLOCK");
         const int v = e ? atoi(e) : 0;
-        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 128;  // 128: 8 192 CTAs for 2^20 integrals, shorter tail (0.286 vs 0.290 ms)
+        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 0;
     }();
-    return dim == 1 ? env1d : 128;
+    if (dim != 1) return 128;
+    if (pinned) return pinned;
+    return dtype == FTS_DD64 ? 256 : 128;
 }
 
 static int launch(const void* fn, long long threads, int block, void* args, cudaStream_t s)
@@ -740,7 +744,7 @@ static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, 
     const int fast = order == FTS_ORDER_REFERENCE ? 0 : (order == FTS_ORDER_FAST ? 1 : 0);
     const void* fn = integrand_kernel(f, t->dtype, KID_FIXED_TPI, fast);
     if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no fixed-grid kernel built for this integrand/dtype/order");
-    return launch(fn, batch, tpi_block(dim), &a, s);
+    return launch(fn, batch, tpi_block(dim, t->dtype), &a, s);
 }
 
 static int check_fixed(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bstride, const void* params,
@@ -1024,7 +1028,7 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
         a.ticket = (unsigned int*)(queue + 1);
         a.tail_idx = queue + 2;
     }
-    if (int rc = launch(fn, batch, tpi_block(dim), &a, s)) return rc;
+    if (int rc = launch(fn, batch, tpi_block(dim, c->dtype), &a, s)) return rc;
     if (fn_tail) {
         const long long cap = (long long)g_prop.multiProcessorCount * 8;
         if (int rc = launch_raw(fn_tail, (unsigned)(batch < cap ? batch : cap), 256, 0, &a, s)) return rc;

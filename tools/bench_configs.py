@@ -245,6 +245,42 @@ def case_e(reps):
              converged=int(r.converged.sum()), max_rel_err_vs_exact_sampled=err)
 
 
+def case_edev(reps):
+    """config E with inputs resident in HBM: kernel-only time (CUDA events) of the Double64 complement kernel"""
+    import torch
+    from fts_b200 import api
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    n = 65536
+    a = -3 * rng.random(n); b = 0.5 + 3.5 * rng.random(n); c = 0.5 + 1.5 * rng.random(n)
+    cache = fts.adaptive_cache_1D(fts.Double64, max_levels=16, complement=True)
+
+    def dd_dev(v):  # [n] float64 -> [n, 2] (hi, lo) = the fts_dd layout
+        return torch.from_numpy(np.stack([v, np.zeros_like(v)], axis=1)).to(dev)
+
+    A, B, Cc = dd_dev(a), dd_dev(b), dd_dev(c)
+    val = torch.empty(n, 2, dtype=torch.float64, device=dev)
+    lev = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, params in (("c_invsqrt", Cc), ("c_log_bmx", None)):
+        f = fts.builtin(name)
+        ts = []
+        for it in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            api.adaptive_batch_dev(cache, f, low=A.data_ptr(), up=B.data_ptr(), bounds_stride=1, params=params.data_ptr() if params is not None else 0,
+                                   params_stride=1 if params is not None else 0, rtol="1e-28", atol=0, max_levels=16, batch=n, value=val.data_ptr(),
+                                   levels=lev.data_ptr(), stream=stream, order="reference", options=1)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        t = min(ts) * 1e-3
+        levels = lev.cpu().numpy()
+        evals = int(evals_for_level(1, levels).sum())
+        emit(case="E-device", family=name, batch=n, ms=t * 1e3, integrals_per_s=n / t, gevals_per_s=evals / t / 1e9, levels=np.bincount(levels).tolist())
+
+
 def main():
     global FP64_PEAK
     ap = argparse.ArgumentParser()
@@ -255,7 +291,7 @@ def main():
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
     emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
     for c in args.cases.split(","):
-        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "Cdev": case_cdev, "D": case_d, "Dk": case_dk, "E": case_e}[c](args.reps)
+        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "Cdev": case_cdev, "D": case_d, "Dk": case_dk, "E": case_e, "Edev": case_edev}[c](args.reps)
 
 
 if __name__ == "__main__":
