@@ -472,6 +472,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
 // evaluates a tile of w_i*(f(x+)+f(x-)) terms in parallel into shared memory, then ONE thread adds
 // them in index order, so the result is bit-identical to the sequential reference loop
 // (adaptive.jl:55-60 / 763-770) while the integrand work is spread over 256 threads.
+// (Double64 tiles are tree-reduced instead, see below.)
 template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bounds__(256) k_adaptive1d_tail(const Args<T> a)
 {
     constexpr int TILE = 1024;
@@ -516,7 +517,22 @@ template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bound
                     }
                 }
                 __syncthreads();
-                if (tid == 0) {
+                if constexpr (sizeof(T) == 16) {
+                    // Double64: a dependent double-double add costs ~160 cycles, so the in-order sum of a
+                    // level-16 integral (131 072 terms) alone takes 10 ms.  Nothing pins the summation
+                    // order of Double64, the tolerance is 1e-28 against a 1e-32 format: the
+                    // tile is reduced by a fixed tree (per-thread strided sums, then halving) instead.
+                    T part = num<T>::zero();
+                    for (int i = tid; i < m; i += blockDim.x) part = part + terms[i];
+                    __syncthreads();
+                    terms[tid] = part;
+                    __syncthreads();
+                    for (int half_n = blockDim.x >> 1; half_n > 0; half_n >>= 1) {
+                        if (tid < half_n) terms[tid] = terms[tid] + terms[tid + half_n];
+                        __syncthreads();
+                    }
+                    if (tid == 0) s_new = s_new + terms[0];
+                } else if (tid == 0) {
                     for (int i = 0; i < m; ++i) s_new = s_new + terms[i];
                 }
                 __syncthreads();
