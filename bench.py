@@ -131,7 +131,13 @@ def cpu_reference(batch_log2: int, steps: int, warmup: int, sample_log2: int, bo
         if bounded and sum(times) > 20.0:
             break
     per_step = sum(times) / len(times)
-    return {"value": sample.size / per_step, "unit": UNIT, "cores": cores, "kind": "port",
+    # the same on ONE core (SURVEY 8d asks for both), on a 16x sparser sample
+    one = np.ascontiguousarray(sample[::16]) if sample.size >= 1024 else sample
+    orc.batch_adaptive1d("f64", FAMILIES["F1_GAUSS"], one, [-1.0], [1.0], RTOL, ATOL, MAX_LEVELS, cache, nthreads=1)
+    t0 = time.perf_counter()
+    orc.batch_adaptive1d("f64", FAMILIES["F1_GAUSS"], one, [-1.0], [1.0], RTOL, ATOL, MAX_LEVELS, cache, nthreads=1)
+    one_core = one.size / (time.perf_counter() - t0)
+    return {"value": sample.size / per_step, "unit": UNIT, "cores": cores, "kind": "port", "value_1core": one_core,
             "sample": f"every {stride}th integral of workload B ({sample.size} integrals, {evals} evals) x {len(times)} passes; "
                       f"oracle/fts_oracle.c ({variant}, OpenMP over the batch, IEEE, no reassociation)",
             "gevals_per_s": evals / per_step / 1e9, "ms_per_step": per_step * 1e3, "steps": len(times)}
@@ -159,7 +165,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": base["steps"],
                 "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config(args.batch_log2, {"cpu_sample": base["sample"]}),
-                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: base[k] for k in ("value", "value_1core", "unit", "cores", "kind", "sample")},
                 "gevals_per_s": base["gevals_per_s"],
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
