@@ -1011,6 +1011,15 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
         }
         return launch_raw(fn_cta, (unsigned)batch, fts::CTA_THREADS, smem_cta, &a, s);
     }
+    // REFERENCE order, 2D/3D, too few integrals to fill the GPU with one thread each: one CTA per
+    // integral evaluates the level's terms in parallel and adds them in the reference's order
+    // (bit-identical to the thread-per-integral kernel, see k_adaptive2d_ord)
+    if (order == FTS_ORDER_REFERENCE && dim >= 2 && !is_dd && batch < 64LL * g_prop.multiProcessorCount) {
+        static const bool use_ord = [] { const char* e = getenv("FTS_B200_ORDERED"); return !e || atoi(e) != 0; }();
+        const void* fn_ord = use_ord ? integrand_kernel(f, c->dtype, KID_ADAPT_ORD, 0) : nullptr;
+        if (fn_ord) return launch_raw(fn_ord, (unsigned)batch, 256, 0, &a, s);
+        if (use_ord) g_last_error.clear();  // families without the kernel fall back to thread per integral
+    }
     const int fast = order == FTS_ORDER_FAST ? 1 : 0;
     const void* fn = integrand_kernel(f, c->dtype, KID_ADAPT_TPI, fast);
     if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no adaptive kernel built for this integrand/dtype/order");

@@ -36,6 +36,14 @@ struct Registrar {
     };                                                                                                               \
     static fts_host::Registrar k_tail_reg_##FUNCTOR(k_tail_entries_##FUNCTOR, 4);
 
+// reference-order cooperative kernels of a 2D / 3D family (CTA per integral, ordered sum), f32 + f64
+#define FTS_REGISTER_ORD(FAM, FUNCTOR, ORD_K)                                                            \
+    static const fts_host::KernelEntry k_ord_entries_##FUNCTOR[] = {                                    \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_ORD, 0, FTS_KPTR(fts::ORD_K<float, fts::FUNCTOR>)},          \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_ORD, 0, FTS_KPTR(fts::ORD_K<double, fts::FUNCTOR>)},         \
+    };                                                                                                   \
+    static fts_host::Registrar k_ord_reg_##FUNCTOR(k_ord_entries_##FUNCTOR, 2);
+
 // adaptive-only families (complement kinds have no exported fixed-grid entry point)
 #define FTS_REGISTER_ADAPT_ONLY(FAM, FUNCTOR, ...)                                                           \
     static const fts_host::KernelEntry k_entries_##FUNCTOR[] = {                                            \

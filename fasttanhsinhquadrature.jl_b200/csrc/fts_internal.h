@@ -18,7 +18,8 @@ enum KernelId : int {
     KID_ADAPT_CTA = 3,     // k_adaptive*_cta              CTA per integral (FAST only)
     KID_LEVEL_GRID = 4,    // k_level*_grid                many CTAs per integral, one launch per level
     KID_ADAPT_TAIL = 5,    // k_adaptive1d_tail               deep levels of queued 1D integrals (reference order)
-    KID_COUNT = 6
+    KID_ADAPT_ORD = 6,     // k_adaptive{2,3}d_ord            CTA per integral, REFERENCE summation order (small 2D/3D batches)
+    KID_COUNT = 7
 };
 
 struct KernelEntry {

@@ -820,4 +820,221 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
 }
 
+// ============================================== reference order at cooperative speed (2D / 3D) ====
+// The scalar 2D/3D kernels of the reference add every term of a level to ONE accumulator in loop
+// order (adaptive.jl:199-209, 430-456), so the sum cannot be split without changing its rounding.
+// What can be split is the evaluation: a CTA owns one integral, its 256 threads evaluate a tile of
+// the level's term SEQUENCE (cell, plane and axis terms at their positions in the loop nest, each by
+// the same device function the thread-per-integral kernel calls), and one thread adds the tile in
+// order.  Bit-identical to k_adaptive{2,3}d_tpi<.., false>; the dependent add (8 cycles per term)
+// replaces a dependent chain of whole integrand evaluations, ~20-50x faster for one integral.
+constexpr int ORD_TILE = 1024;
+
+// adds terms[0..m) in index order to s (thread 0 only), with CTA barriers on both sides
+template <class T> __device__ __forceinline__ void ordered_add_tile(T& s, const T* terms, int m)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 4
+        for (int i = 0; i < m; ++i) s = s + terms[i];
+    }
+    __syncthreads();
+}
+
+// term `pos` of level-l sequence of the 2D loop nest: for i = 1..n { cells (i, j), j = 1..n (all j
+// if i is odd, odd j otherwise); axis term of i if i is odd }
+template <class T, class F, bool CMPL> __device__ __forceinline__ T term2d(const Args<T>& a, const Box2<T>& bx, const T* p, int n, long long pos)
+{
+    const int off = n - 4;
+    const int P = n + 1 + (n >> 1);  // an odd row (n cells + axis) followed by an even row (n/2 cells)
+    const int q = (int)(pos / P), r = (int)(pos - (long long)q * P);
+    int i, j;
+    bool axis = false;
+    if (r <= n) {
+        i = 2 * q + 1;
+        j = r + 1;
+        axis = r == n;
+    } else {
+        i = 2 * q + 2;
+        j = 2 * (r - (n + 1)) + 1;
+    }
+    if constexpr (CMPL) {
+        const NodeC<T> ni = a.nodes_c[off + i - 1];
+        if (axis) return axes2_c<T, F, false>(bx, p, ni.x, ni.c, ni.w);
+        const NodeC<T> nj = a.nodes_c[off + j - 1];
+        return quadrants_c<T, F, false>(bx, p, ni.x, ni.c, nj.x, nj.c, ni.w, nj.w);
+    } else {
+        const Node<T> ni = ldg_node(a.nodes + off + i - 1);
+        if (axis) return axes2<T, F, false>(bx, p, ni.x, ni.w);
+        const Node<T> nj = ldg_node(a.nodes + off + j - 1);
+        return quadrants<T, F, false>(bx, p, ni.x, nj.x, ni.w, nj.w);
+    }
+}
+
+// adaptive_integrate_2D typed core, reference order, one CTA per integral   adaptive.jl:154-224
+template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive2d_ord(const Args<T> a)
+{
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    __shared__ T terms[ORD_TILE];
+    __shared__ int s_done;
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[2], hi[2];
+    bool neg;
+    int flags;
+    if (!load_box<2>(a, b, lo, hi, neg, flags)) {
+        if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        return;
+    }
+    const T half = num<T>::half();
+    Box2<T> bx;
+    bx.dx = half * (hi[0] - lo[0]); bx.x0 = half * (hi[0] + lo[0]);
+    bx.dy = half * (hi[1] - lo[1]); bx.y0 = half * (hi[1] + lo[1]);
+    bx.w0 = num<T>::half_pi();
+    T h = a.tm * half;
+    T s_total = num<T>::zero();
+    if (tid == 0) {  // level 0 exactly as k_adaptive2d_tpi (25 evaluations)
+        const T w02 = bx.w0 * bx.w0;
+        if constexpr (CMPL) s_total = w02 * F::template eval<T, false>(bx.x0, bx.y0, bx.dx, bx.dx, bx.dy, bx.dy, p);
+        else s_total = w02 * F::template eval<T, false>(bx.x0, bx.y0, p);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if constexpr (CMPL) s_total = s_total + quadrants_c<T, F, false>(bx, p, a.ix[i], a.ic[i], a.ix[j], a.ic[j], a.iw[i], a.iw[j]);
+                else s_total = s_total + quadrants<T, F, false>(bx, p, a.ix[i], a.ix[j], a.iw[i], a.iw[j]);
+            }
+            if constexpr (CMPL) s_total = s_total + axes2_c<T, F, false>(bx, p, a.ix[i], a.ic[i], a.iw[i]);
+            else s_total = s_total + axes2<T, F, false>(bx, p, a.ix[i], a.iw[i]);
+        }
+    }
+    T old_res = bx.dx * bx.dy * (h * h) * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 2 << level;
+        const long long nterms = (long long)(n >> 1) * (n + 1 + (n >> 1));
+        T s_new = num<T>::zero();
+        for (long long t0 = 0; t0 < nterms; t0 += ORD_TILE) {
+            const int m = (int)(nterms - t0 < ORD_TILE ? nterms - t0 : ORD_TILE);
+            for (int i = tid; i < m; i += blockDim.x) terms[i] = term2d<T, F, CMPL>(a, bx, p, n, t0 + i);
+            ordered_add_tile(s_new, terms, m);
+        }
+        if (tid == 0) {
+            s_total = s_total + s_new;
+            const T new_res = bx.dx * bx.dy * (h * h) * s_total;
+            err = fm::abs(new_res - old_res);
+            level_used = level;
+            old_res = new_res;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            if (conv) flags |= FLAG_CONVERGED;
+            s_done = conv ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
+// term `pos` of the 3D loop nest: for i { for j { cells (i,j,k): all k if i or j is odd, odd k
+// otherwise; plane term of (i,j) if i or j is odd }; axis term of i if i is odd }
+template <class T, class F> __device__ __forceinline__ T term3d(const Args<T>& a, const Box3<T>& bx, const T* p, int n, long long pos)
+{
+    const Node<T>* __restrict__ lv = a.nodes + (n - 4);
+    const long long b_odd = (long long)n * (n + 1) + 1;          // odd i: n full rows + the axis term
+    const int R = (n + 1) + (n >> 1);                            // even i: a full row (odd j) + a half row (even j)
+    const long long b_even = (long long)(n >> 1) * R;
+    const long long B = b_odd + b_even;
+    const long long qi = pos / B;
+    long long r = pos - qi * B;
+    int i, j, k;
+    bool plane = false;
+    if (r < b_odd) {
+        i = (int)(2 * qi + 1);
+        if (r == b_odd - 1) {
+            const Node<T> ni = ldg_node(lv + i - 1);
+            return axes3<T, F, false>(bx, p, ni.x, ni.w);
+        }
+        j = (int)(r / (n + 1)) + 1;
+        const int rr = (int)(r - (long long)(j - 1) * (n + 1));
+        plane = rr == n;
+        k = rr + 1;
+    } else {
+        r -= b_odd;
+        i = (int)(2 * qi + 2);
+        const int qj = (int)(r / R), r2 = (int)(r - (long long)qj * R);
+        if (r2 <= n) {
+            j = 2 * qj + 1;
+            plane = r2 == n;
+            k = r2 + 1;
+        } else {
+            j = 2 * qj + 2;
+            k = 2 * (r2 - (n + 1)) + 1;
+        }
+    }
+    const Node<T> ni = ldg_node(lv + i - 1), nj = ldg_node(lv + j - 1);
+    if (plane) return planes<T, F, false>(bx, p, ni.x, nj.x, ni.w, nj.w);
+    const Node<T> nk = ldg_node(lv + k - 1);
+    return octant<T, F, false>(bx, p, ni.x, nj.x, nk.x, ni.w, nj.w, nk.w);
+}
+
+// adaptive_integrate_3D typed core, reference order, one CTA per integral   adaptive.jl:352-471
+template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_ord(const Args<T> a)
+{
+    __shared__ T terms[ORD_TILE];
+    __shared__ int s_done;
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[3], hi[3];
+    bool neg;
+    int flags;
+    if (!load_box<3>(a, b, lo, hi, neg, flags)) {
+        if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        return;
+    }
+    const T half = num<T>::half();
+    const Box3<T> bx = make_box3(lo, hi);
+    T h = a.tm * half;
+    T s_total = num<T>::zero();
+    if (tid == 0) s_total = level0_3d<T, F, false>(bx, p, a.ix, a.iw);
+    T old_res = bx.dx * bx.dy * bx.dz * (h * h * h) * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 2 << level;
+        const long long nterms = (long long)(n >> 1) * ((long long)n * (n + 1) + 1 + (long long)(n >> 1) * ((n + 1) + (n >> 1)));
+        T s_new = num<T>::zero();
+        for (long long t0 = 0; t0 < nterms; t0 += ORD_TILE) {
+            const int m = (int)(nterms - t0 < ORD_TILE ? nterms - t0 : ORD_TILE);
+            for (int i = tid; i < m; i += blockDim.x) terms[i] = term3d<T, F>(a, bx, p, n, t0 + i);
+            ordered_add_tile(s_new, terms, m);
+        }
+        if (tid == 0) {
+            s_total = s_total + s_new;
+            const T new_res = bx.dx * bx.dy * bx.dz * (h * h * h) * s_total;
+            err = fm::abs(new_res - old_res);
+            level_used = level;
+            old_res = new_res;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            if (conv) flags |= FLAG_CONVERGED;
+            s_done = conv ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
 }  // namespace fts

@@ -455,6 +455,52 @@ def test_adaptive_2d_warp_per_integral_and_queue(gpu, oracle):
     assert rm.converged.all() and rel(rm.value[keep], ex[keep]).max() < 1e-9
 
 
+def test_reference_order_cooperative_kernels_match_thread_per_integral(gpu, oracle):
+    """Small 2D/3D batches in reference order run one CTA per integral (terms evaluated in parallel,
+    added in the reference's loop order); batches of >= 64 x SMs integrals run one thread per
+    integral.  Same arithmetic, same order -> the same bits, including levels, errors and flags."""
+    nbig = 64 * gpu.device_info()["sm_count"] + 128
+    rng = np.random.default_rng(21)
+    # 2D: smooth, endpoint-singular and complement integrands, boxes of different sizes
+    c2 = gpu.adaptive_cache_2D(np.float64, max_levels=8)
+    low = np.stack([-1 - rng.random(nbig), -1 - rng.random(nbig)], axis=1)
+    up = np.stack([1 + rng.random(nbig), 0.5 + rng.random(nbig)], axis=1)
+    low[3], up[3] = (0.5, -1.0), (0.5, 1.0)           # zero width
+    low[4], up[4] = (1.0, -1.0), (-0.5, 1.0)          # flipped
+    for name, lo_, up_, kw in (("exp_2d", low, up, dict(rtol=1e-9)), ("x2py2", low, up, dict(rtol=1e-12)),
+                               ("invsqrt_2d", np.full((nbig, 2), -1.0), np.full((nbig, 2), 1.0), dict(rtol=1e-7))):
+        big = gpu.quad(gpu.builtin(name), lo_, up_, max_levels=8, cache=c2, order="reference", full_output=True, **kw)
+        small = gpu.quad(gpu.builtin(name), lo_[:300], up_[:300], max_levels=8, cache=c2, order="reference", full_output=True, **kw)
+        for fld in ("value", "err", "levels", "flags"):
+            assert np.array_equal(getattr(small, fld), getattr(big, fld)[:300]), (name, fld)
+    cc = gpu.adaptive_cache_2D_cmpl(np.float64, max_levels=8)
+    blo = np.stack([-3 + 2 * rng.random(nbig), -3 + 2 * rng.random(nbig)], axis=1)
+    bup = np.stack([1 + 2 * rng.random(nbig), 1 + 2 * rng.random(nbig)], axis=1)
+    f = gpu.builtin("c2_invsqrt_bmx_ymc")
+    big = gpu.quad_cmpl(f, blo, bup, rtol=1e-10, max_levels=8, cache=cc, order="reference", full_output=True)
+    small = gpu.quad_cmpl(f, blo[:200], bup[:200], rtol=1e-10, max_levels=8, cache=cc, order="reference", full_output=True)
+    assert np.array_equal(small.value, big.value[:200]) and np.array_equal(small.levels, big.levels[:200])
+    # 3D (levels 3-4: up to 2.7e5 evaluations per integral), Float64 and Float32
+    for T, rt in ((np.float64, 1e-8), (np.float32, 1e-4)):
+        c3 = gpu.adaptive_cache_3D(T, max_levels=5)
+        l3 = np.stack([-1 - rng.random(nbig), -1 - rng.random(nbig), -rng.random(nbig)], axis=1).astype(T)
+        u3 = np.stack([1 + rng.random(nbig), 0.5 + rng.random(nbig), 1 + rng.random(nbig)], axis=1).astype(T)
+        for name in ("exp_3d", "x2y2z2"):
+            big = gpu.adaptive_integrate_3D(T, gpu.builtin(name), l3, u3, rtol=rt, max_levels=5, cache=c3, order="reference", full_output=True)
+            small = gpu.adaptive_integrate_3D(T, gpu.builtin(name), l3[:100], u3[:100], rtol=rt, max_levels=5, cache=c3, order="reference",
+                                              full_output=True)
+            for fld in ("value", "err", "levels", "flags"):
+                assert np.array_equal(getattr(small, fld), getattr(big, fld)[:100]), (name, T, fld)
+    # and against the oracle's sequential loop directly (one deep integral: level 6 = 1.7e7 evaluations)
+    c3 = gpu.adaptive_cache_3D(np.float64, max_levels=6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        v = gpu.adaptive_integrate_3D(np.float64, gpu.builtin("rat_3d"), [0.0, 0.0, 0.0], [1.0, 2.0, 1.5], rtol=1e-13, max_levels=6, cache=c3,
+                                      order="reference", full_output=True)
+    ref = oracle.adaptive_nd("f64", 3, F["F3_RAT"], None, [0.0, 0.0, 0.0], [1.0, 2.0, 1.5], 1e-13, 0.0, 6, oracle.cache_tensor("f64", 3, 6))
+    assert v.levels[0] == ref.level and rel(v.value[0], ref.value) <= 2e-16
+
+
 def test_adaptive_3d_orders(gpu, oracle):
     oc = oracle.cache_tensor("f64", 3, 6)
     cache = gpu.adaptive_cache_3D(np.float64, max_levels=6)
