@@ -44,6 +44,13 @@ struct Registrar {
     };                                                                                                   \
     static fts_host::Registrar k_ord_reg_##FUNCTOR(k_ord_entries_##FUNCTOR, 2);
 
+#define FTS_REGISTER_FIXED_ORD(FAM, FUNCTOR, ORD_K)                                                      \
+    static const fts_host::KernelEntry k_ford_entries_##FUNCTOR[] = {                                   \
+        {FAM, FTS_F32, fts_host::KID_FIXED_ORD, 0, FTS_KPTR(fts::ORD_K<float, fts::FUNCTOR>)},          \
+        {FAM, FTS_F64, fts_host::KID_FIXED_ORD, 0, FTS_KPTR(fts::ORD_K<double, fts::FUNCTOR>)},         \
+    };                                                                                                   \
+    static fts_host::Registrar k_ford_reg_##FUNCTOR(k_ford_entries_##FUNCTOR, 2);
+
 // adaptive-only families (complement kinds have no exported fixed-grid entry point)
 #define FTS_REGISTER_ADAPT_ONLY(FAM, FUNCTOR, ...)                                                           \
     static const fts_host::KernelEntry k_entries_##FUNCTOR[] = {                                            \

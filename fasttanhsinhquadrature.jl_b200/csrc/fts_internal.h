@@ -19,7 +19,8 @@ enum KernelId : int {
     KID_LEVEL_GRID = 4,    // k_level*_grid                many CTAs per integral, one launch per level
     KID_ADAPT_TAIL = 5,    // k_adaptive1d_tail               deep levels of queued 1D integrals (reference order)
     KID_ADAPT_ORD = 6,     // k_adaptive{2,3}d_ord            CTA per integral, REFERENCE summation order (small 2D/3D batches)
-    KID_COUNT = 7
+    KID_FIXED_ORD = 7,     // k_fixed{2,3}d_ord               CTA per integral, REFERENCE order (small 2D/3D batches)
+    KID_COUNT = 8
 };
 
 struct KernelEntry {

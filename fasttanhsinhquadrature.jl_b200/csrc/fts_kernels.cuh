@@ -1037,4 +1037,121 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
     }
 }
 
+// ---- fixed grids in reference order, one CTA per integral --------------------------------------
+// integrate2D / integrate3D (integrate2D.jl:91-124, integrate3D.jl:150-207) sum row by row: an inner
+// sum over j (2D) or k (3D) per row, rows folded into the total in loop order.  Rows are independent,
+// so every thread walks whole rows with the inner loop of k_fixed{2,3}d_tpi, the row results go to
+// shared memory, and one thread folds them in order: bit-identical, and the dependent chain is one
+// row instead of the whole grid (one integrate3D at N = 256: 17 M evaluations, 0.35 s on one thread).
+constexpr int ORD_ROWS = 1024;
+
+template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord(const Args<T> a)
+{
+    __shared__ T rows[ORD_ROWS];
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T* lo = a.low + b * a.bstride;
+    const T* hi = a.up + b * a.bstride;
+    const T dx = half * (hi[0] - lo[0]), x0 = half * (hi[0] + lo[0]);
+    const T dy = half * (hi[1] - lo[1]), y0 = half * (hi[1] + lo[1]);
+    const T w0 = num<T>::half_pi();
+    const T w02 = w0 * w0;
+    const int n = a.n;
+    T s = num<T>::zero();
+    if (tid == 0) s = w02 * F::template eval<T, false>(x0, y0, p);
+    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {  // axis terms
+        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
+        for (int r = tid; r < m; r += blockDim.x) {
+            const Node<T> nd = ldg_node(a.grid + c0 + r);
+            const T xkp = dx * nd.x + x0, xkm = x0 - dx * nd.x;
+            const T ykp = dy * nd.x + y0, ykm = y0 - dy * nd.x;
+            rows[r] = nd.w * w0 * (F::template eval<T, false>(xkp, y0, p) + F::template eval<T, false>(xkm, y0, p) +
+                                   F::template eval<T, false>(x0, ykp, p) + F::template eval<T, false>(x0, ykm, p));
+        }
+        ordered_add_tile(s, rows, m);
+    }
+    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {  // quadrant rows
+        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
+        for (int r = tid; r < m; r += blockDim.x) {
+            const Node<T> ni = ldg_node(a.grid + c0 + r);
+            const T xip = dx * ni.x + x0, xim = x0 - dx * ni.x;
+            T inner = num<T>::zero();
+            for (int j = 0; j < n; ++j) {
+                const Node<T> nj = ldg_node(a.grid + j);
+                const T yjp = dy * nj.x + y0, yjm = y0 - dy * nj.x;
+                inner = inner + nj.w * (F::template eval<T, false>(xim, yjm, p) + F::template eval<T, false>(xip, yjm, p) +
+                                        F::template eval<T, false>(xim, yjp, p) + F::template eval<T, false>(xip, yjp, p));
+            }
+            rows[r] = ni.w * inner;
+        }
+        ordered_add_tile(s, rows, m);
+    }
+    if (tid == 0) a.value[b] = dx * dy * (a.h * a.h) * s;
+}
+
+template <class T, class F> __global__ void __launch_bounds__(256) k_fixed3d_ord(const Args<T> a)
+{
+    __shared__ T rows[2 * ORD_ROWS];  // (plane term, octant term) per (i, j)
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T* lo = a.low + b * a.bstride;
+    const T* hi = a.up + b * a.bstride;
+    const T dx = half * (hi[0] - lo[0]), x0 = half * (hi[0] + lo[0]);
+    const T dy = half * (hi[1] - lo[1]), y0 = half * (hi[1] + lo[1]);
+    const T dz = half * (hi[2] - lo[2]), z0 = half * (hi[2] + lo[2]);
+    const T w0 = num<T>::half_pi();
+    const T w02 = w0 * w0;
+    const T w03 = w02 * w0;
+    const int n = a.n;
+#define FE(X, Y, Z) F::template eval<T, false>(X, Y, Z, p)
+    T total = num<T>::zero();
+    if (tid == 0) total = w03 * FE(x0, y0, z0);
+    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {  // axis terms
+        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
+        for (int r = tid; r < m; r += blockDim.x) {
+            const Node<T> nd = ldg_node(a.grid + c0 + r);
+            const T axis = (FE(dx * nd.x + x0, y0, z0) + FE(x0 - dx * nd.x, y0, z0)) + (FE(x0, dy * nd.x + y0, z0) + FE(x0, y0 - dy * nd.x, z0)) +
+                           (FE(x0, y0, dz * nd.x + z0) + FE(x0, y0, z0 - dz * nd.x));
+            rows[r] = nd.w * w02 * axis;
+        }
+        ordered_add_tile(total, rows, m);
+    }
+    const long long npair = (long long)n * n;
+    for (long long c0 = 0; c0 < npair; c0 += ORD_ROWS) {  // (i, j) rows: plane term, then the octant row sum
+        const int m = (int)(npair - c0 < ORD_ROWS ? npair - c0 : ORD_ROWS);
+        for (int r = tid; r < m; r += blockDim.x) {
+            const long long q = c0 + r;
+            const int i = (int)(q / n), j = (int)(q - (long long)i * n);
+            const Node<T> ni = ldg_node(a.grid + i);
+            const T xp = dx * ni.x + x0, xm = x0 - dx * ni.x;
+            const T ypi = dy * ni.x + y0, ymi = y0 - dy * ni.x;
+            const Node<T> nj = ldg_node(a.grid + j);
+            const T wiwj = ni.w * nj.w;
+            const T yp = dy * nj.x + y0, ym = y0 - dy * nj.x;
+            const T zpj = dz * nj.x + z0, zmj = z0 - dz * nj.x;
+            const T plane = (FE(xp, yp, z0) + FE(xm, yp, z0) + FE(xp, ym, z0) + FE(xm, ym, z0)) +
+                            (FE(xp, y0, zpj) + FE(xm, y0, zpj) + FE(xp, y0, zmj) + FE(xm, y0, zmj)) +
+                            (FE(x0, ypi, zpj) + FE(x0, ymi, zpj) + FE(x0, ypi, zmj) + FE(x0, ymi, zmj));
+            rows[2 * r] = wiwj * w0 * plane;
+            T oct = num<T>::zero();
+            for (int k = 0; k < n; ++k) {
+                const Node<T> nk = ldg_node(a.grid + k);
+                const T zp = dz * nk.x + z0, zm = z0 - dz * nk.x;
+                oct = oct + nk.w * ((FE(xp, yp, zp) + FE(xm, yp, zp) + FE(xp, ym, zp) + FE(xm, ym, zp)) +
+                                    (FE(xp, yp, zm) + FE(xm, yp, zm) + FE(xp, ym, zm) + FE(xm, ym, zm)));
+            }
+            rows[2 * r + 1] = wiwj * oct;
+        }
+        ordered_add_tile(total, rows, 2 * m);
+    }
+#undef FE
+    if (tid == 0) a.value[b] = (dx * dy * dz * (a.h * a.h * a.h)) * total;
+}
+
 }  // namespace fts

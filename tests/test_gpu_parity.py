@@ -491,6 +491,17 @@ def test_reference_order_cooperative_kernels_match_thread_per_integral(gpu, orac
                                               full_output=True)
             for fld in ("value", "err", "levels", "flags"):
                 assert np.array_equal(getattr(small, fld), getattr(big, fld)[:100]), (name, T, fld)
+    # fixed grids: integrate2D / integrate3D row sums (rows in parallel, folded in order)
+    x, w, h = gpu.tanhsinh(np.float64, 40)
+    for name, lo_, up_, fn in (("exp_2d", low, up, gpu.integrate2D), ("invsqrt_2d", np.full((nbig, 2), -1.0), np.full((nbig, 2), 1.0), gpu.integrate2D),
+                               ("exp_3d", l3.astype(np.float64), u3.astype(np.float64), gpu.integrate3D),
+                               ("x2y2z2", l3.astype(np.float64), u3.astype(np.float64), gpu.integrate3D)):
+        big = fn(gpu.builtin(name), lo_, up_, x, w, h, order="reference")
+        small = fn(gpu.builtin(name), lo_[:150], up_[:150], x, w, h, order="reference")
+        assert np.array_equal(small, big[:150]), name
+    x3, w3, h3 = gpu.tanhsinh(np.float64, 128)
+    v = gpu.integrate3D(gpu.builtin("exp_3d"), [-1.0] * 3, [1.0] * 3, x3, w3, h3, order="reference")      # 2.1e6 evaluations, one CTA
+    assert rel(v, (math.e - 1 / math.e) ** 3) <= 1e-13
     # and against the oracle's sequential loop directly (one deep integral: level 6 = 1.7e7 evaluations)
     c3 = gpu.adaptive_cache_3D(np.float64, max_levels=6)
     with warnings.catch_warnings():
