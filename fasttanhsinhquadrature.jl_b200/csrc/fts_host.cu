@@ -742,7 +742,8 @@ static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, 
     if (batch == 0) return FTS_OK;
     if (st == STYLE_CTA) return launch_raw(fn_cta, (unsigned)batch, fts::CTA_THREADS, smem, &a, s);
     // REFERENCE order on a few 2D/3D integrals: rows in parallel, folded in order (k_fixed2d_ord)
-    if (order == FTS_ORDER_REFERENCE && dim >= 2 && t->dtype != FTS_DD64 && batch < 64LL * g_prop.multiProcessorCount) {
+    // (1D: only long grids — a thread adds 2 x 256 evaluations faster than a CTA can be scheduled)
+    if (order == FTS_ORDER_REFERENCE && (dim >= 2 || t->n >= 256) && t->dtype != FTS_DD64 && batch < 64LL * g_prop.multiProcessorCount) {
         static const bool use_ord = [] { const char* e = getenv("FTS_B200_ORDERED"); return !e || atoi(e) != 0; }();
         const void* fn_ord = use_ord ? integrand_kernel(f, t->dtype, KID_FIXED_ORD, 0) : nullptr;
         if (fn_ord) return launch_raw(fn_ord, (unsigned)batch, 256, 0, &a, s);

@@ -1045,6 +1045,33 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
 // row instead of the whole grid (one integrate3D at N = 256: 17 M evaluations, 0.35 s on one thread).
 constexpr int ORD_ROWS = 1024;
 
+// integrate1D in reference order (integrate1D.jl:90-102): terms in parallel, added in order
+template <class T, class F> __global__ void __launch_bounds__(256) k_fixed1d_ord(const Args<T> a)
+{
+    __shared__ T rows[ORD_ROWS];
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    const T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    const int n = a.n;
+    T s = num<T>::zero();
+    if (tid == 0) s = num<T>::half_pi() * F::template eval<T, false>(x0, p);
+    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {
+        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
+        for (int r = tid; r < m; r += blockDim.x) {
+            const Node<T> nd = ldg_node(a.grid + c0 + r);
+            const T d = dx * nd.x;
+            const T xm = x0 - d, xp = x0 + d;
+            rows[r] = nd.w * (F::template eval<T, false>(xm, p) + F::template eval<T, false>(xp, p));
+        }
+        ordered_add_tile(s, rows, m);
+    }
+    if (tid == 0) a.value[b] = dx * a.h * s;
+}
+
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord(const Args<T> a)
 {
     __shared__ T rows[ORD_ROWS];

@@ -99,6 +99,7 @@ void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
                 v.push_back({dt, KID_LEVEL_GRID, 1, std::string("fts::k_level_grid<") + tn[dt] + ", FtsUserIntegrand, 3>"});
             if (kind == FTS_KIND_2D || kind == FTS_KIND_2D_CMPL) v.push_back({dt, KID_ADAPT_ORD, 0, std::string("fts::k_adaptive2d_ord") + targs});
             if (kind == FTS_KIND_3D) v.push_back({dt, KID_ADAPT_ORD, 0, std::string("fts::k_adaptive3d_ord") + targs});
+            if (kind == FTS_KIND_1D) v.push_back({dt, KID_FIXED_ORD, 0, std::string("fts::k_fixed1d_ord") + targs});
             if (kind == FTS_KIND_2D) v.push_back({dt, KID_FIXED_ORD, 0, std::string("fts::k_fixed2d_ord") + targs});
             if (kind == FTS_KIND_3D) v.push_back({dt, KID_FIXED_ORD, 0, std::string("fts::k_fixed3d_ord") + targs});
         }

@@ -499,6 +499,13 @@ def test_reference_order_cooperative_kernels_match_thread_per_integral(gpu, orac
         big = fn(gpu.builtin(name), lo_, up_, x, w, h, order="reference")
         small = fn(gpu.builtin(name), lo_[:150], up_[:150], x, w, h, order="reference")
         assert np.array_equal(small, big[:150]), name
+    x1, w1, h1 = gpu.tanhsinh(np.float64, 2600)        # 1D: long grids only (n >= 256), two tiles + a remainder
+    lo1, up1 = -1 - rng.random(nbig), 1 + rng.random(nbig)
+    for name, par in (("exp", None), ("runge", np.full((nbig, 1), 25.0)), ("log1mx", None)):
+        lo_, up_ = (lo1, up1) if name != "log1mx" else (np.full(nbig, -1.0), np.full(nbig, 1.0))
+        big = gpu.integrate1D(gpu.builtin(name), lo_, up_, x1, w1, h1, params=par, order="reference")
+        small = gpu.integrate1D(gpu.builtin(name), lo_[:150], up_[:150], x1, w1, h1, params=None if par is None else par[:150], order="reference")
+        assert np.array_equal(small, big[:150]), name
     x3, w3, h3 = gpu.tanhsinh(np.float64, 128)
     v = gpu.integrate3D(gpu.builtin("exp_3d"), [-1.0] * 3, [1.0] * 3, x3, w3, h3, order="reference")      # 2.1e6 evaluations, one CTA
     assert rel(v, (math.e - 1 / math.e) ** 3) <= 1e-13
