@@ -33,14 +33,19 @@ RTOL, ATOL, MAX_LEVELS = 1e-10, 0.0, 16
 FP64_THEORETICAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2
 
 
+PERMUTE = False  # --permute: the same alpha set shuffled with seed 0 (SURVEY §8(d) names both orders)
+
+
 def workload(batch_log2: int):
     n = 1 << batch_log2
     alpha = 0.5 + 49.5 * np.arange(n, dtype=np.float64) / (n - 1)  # SURVEY §8(d) synthetic input B
+    if PERMUTE:
+        alpha = alpha[np.random.default_rng(0).permutation(n)]
     return n, alpha
 
 
 def config(batch_log2: int, extra=None):
-    c = {"workload": f"B: 2^{batch_log2} adaptive quad of exp(-a*x^2) on [-1,1], a in [0.5,50] (sorted sweep), rtol=1e-10, atol=0, "
+    c = {"workload": f"B: 2^{batch_log2} adaptive quad of exp(-a*x^2) on [-1,1], a in [0.5,50] ({'permuted, seed 0' if PERMUTE else 'sorted sweep'}), rtol=1e-10, atol=0, "
                      f"max_levels=16, Float64, reference summation order (quad semantics)",
          "batch_per_gpu": 1 << batch_log2, "l2_policy": "256 MiB L2 flush between timed steps (inputs are 8 MiB < L2)"}
     if extra:
@@ -152,8 +157,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-log2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--permute", action="store_true", help="shuffle the alpha sweep (seed 0): lanes of a warp then stop at different levels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global PERMUTE
+    PERMUTE = args.permute
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
