@@ -56,8 +56,10 @@ typedef struct { double hi, lo; } fts_dd;
 /* ---- summation order --------------------------------------------------------------------- */
 typedef enum {
     /* exact sequential order of the reference's scalar kernels (what quad/quad_cmpl/quad_split
-       and integrate*D / adaptive_integrate_* compute; quad.jl:49,117,155,309): one thread per
-       integral, no FMA contraction. */
+       and integrate*D / adaptive_integrate_* compute; quad.jl:49,117,155,309), no FMA
+       contraction: one thread per integral for large batches; for a few 2D/3D integrals (and
+       long 1D grids) one CTA per integral evaluates the terms in parallel and adds them in the
+       same order — bit-identical results either way. */
     FTS_ORDER_REFERENCE = 0,
     /* reassociated + FMA, compensated merges (the analogue of the `_avx`/@turbo twins,
        integrate1D.jl:124-147, adaptive.jl:94-133 ...): cooperative CTA/grid per integral. */
