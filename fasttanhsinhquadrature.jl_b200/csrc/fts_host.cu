@@ -670,6 +670,36 @@ static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, voi
     return FTS_OK;
 }
 
+// one cluster of `csize` CTAs (thread-block cluster, distributed shared memory) per work item
+static int launch_cluster(const void* fn, unsigned nclusters, unsigned csize, int block, size_t smem, void* args, cudaStream_t s)
+{
+    if (smem > 40 * 1024) {
+        if (smem > dyn_smem_limit()) return set_error(FTS_ERR_UNSUPPORTED, "launch needs more shared memory than a CTA has");
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            FTS_CUDA(cudaKernelSetAttributeForDevice((cudaKernel_t)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, g_device));
+        }
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(nclusters * csize);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = csize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    void* params[] = {args};
+    FTS_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
+    g_launches.fetch_add(1);
+    return FTS_OK;
+}
+
 // threads per CTA of the 1D thread-per-integral kernels: 128 (8 192 CTAs for 2^20 Float64
 // integrals: shorter tail than 256, 0.286 vs 0.290 ms on config B); Double64 prefers 256 (config E
 // 0.378 vs 0.394 ms); smaller CTAs for small batches were measured and do not help.
@@ -1025,7 +1055,16 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     if (order == FTS_ORDER_REFERENCE && dim >= 2 && !is_dd && batch < 64LL * g_prop.multiProcessorCount) {
         static const bool use_ord = [] { const char* e = getenv("FTS_B200_ORDERED"); return !e || atoi(e) != 0; }();
         const void* fn_ord = use_ord ? integrand_kernel(f, c->dtype, KID_ADAPT_ORD, 0) : nullptr;
-        if (fn_ord) return launch_raw(fn_ord, (unsigned)batch, 256, 0, &a, s);
+        if (fn_ord) {
+            // clusters of 8/4/2 CTAs when the integrals are too few to occupy the SMs one CTA each
+            static const int max_cluster = [] { const char* e = getenv("FTS_B200_ORD_CLUSTER"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+            unsigned csize = 1;
+            while ((int)csize * 2 <= max_cluster && batch * (long long)csize * 2 <= 2LL * g_prop.multiProcessorCount) csize *= 2;
+            // tile buffers: 2 x 4096 terms for a few integrals (the evaluation of a whole tile overlaps
+            // the add of the previous one), 2 x 1024 when there are CTAs to spare (16 KiB: more CTAs per SM)
+            a.level = batch >= g_prop.multiProcessorCount ? 1024 : 4096;
+            return launch_cluster(fn_ord, (unsigned)batch, csize, 256, 2 * (size_t)a.level * sizeof(T), &a, s);
+        }
         if (use_ord) g_last_error.clear();  // families without the kernel fall back to thread per integral
     }
     const int fast = order == FTS_ORDER_FAST ? 1 : 0;
