@@ -776,7 +776,12 @@ static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, 
     if (order == FTS_ORDER_REFERENCE && (dim >= 2 || t->n >= 256) && t->dtype != FTS_DD64 && batch < 64LL * g_prop.multiProcessorCount) {
         static const bool use_ord = [] { const char* e = getenv("FTS_B200_ORDERED"); return !e || atoi(e) != 0; }();
         const void* fn_ord = use_ord ? integrand_kernel(f, t->dtype, KID_FIXED_ORD, 0) : nullptr;
-        if (fn_ord) return launch_raw(fn_ord, (unsigned)batch, 256, 0, &a, s);
+        if (fn_ord) {
+            unsigned csize = 1;  // a cluster of CTAs per integral when the integrals are too few to occupy the SMs
+            while (csize < 8 && batch * (long long)csize * 2 <= 2LL * g_prop.multiProcessorCount) csize *= 2;
+            a.level = 4096;  // terms per tile buffer: with 8 x 256 threads every thread gets a 3D row per tile
+            return launch_cluster(fn_ord, (unsigned)batch, csize, 256, 2 * (size_t)a.level * sizeof(T), &a, s);
+        }
         if (use_ord) g_last_error.clear();
     }
     const int fast = order == FTS_ORDER_REFERENCE ? 0 : (order == FTS_ORDER_FAST ? 1 : 0);

@@ -828,7 +828,6 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
 // the same device function the thread-per-integral kernel calls), and one thread adds the tile in
 // order.  Bit-identical to k_adaptive{2,3}d_tpi<.., false>; the dependent add (8 cycles per term)
 // replaces a dependent chain of whole integrand evaluations, ~20-50x faster for one integral.
-constexpr int ORD_TILE = 1024;
 
 // s += terms[0] + terms[1] + ... in index order, one thread.  The chain of dependent adds is the
 // whole cost, so the loads run eight terms ahead of it (a plain loop exposes the shared-memory
@@ -922,13 +921,6 @@ template <class T, class TermFn> __device__ __forceinline__ void ordered_sum_clu
     }
 }
 
-// adds terms[0..m) in index order to s (thread 0 only), with CTA barriers on both sides
-template <class T> __device__ __forceinline__ void ordered_add_tile(T& s, const T* terms, int m)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) ordered_add(s, terms, m);
-    __syncthreads();
-}
 
 // term `pos` of level-l sequence of the 2D loop nest: for i = 1..n { cells (i, j), j = 1..n (all j
 // if i is odd, odd j otherwise); axis term of i if i is odd }
@@ -1126,40 +1118,34 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
 // so every thread walks whole rows with the inner loop of k_fixed{2,3}d_tpi, the row results go to
 // shared memory, and one thread folds them in order: bit-identical, and the dependent chain is one
 // row instead of the whole grid (one integrate3D at N = 256: 17 M evaluations, 0.35 s on one thread).
-constexpr int ORD_ROWS = 1024;
 
 // integrate1D in reference order (integrate1D.jl:90-102): terms in parallel, added in order
+// (cluster machinery of ordered_sum_cluster: one cluster of 1..8 CTAs per integral)
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed1d_ord(const Args<T> a)
 {
-    __shared__ T rows[ORD_ROWS];
-    const long long b = blockIdx.x;
-    const int tid = threadIdx.x;
+    const long long b = cluster_id_x();
+    const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, b);
     const T half = num<T>::half();
     const T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
     const T dx = half * (hi - lo), x0 = half * (hi + lo);
-    const int n = a.n;
     T s = num<T>::zero();
-    if (tid == 0) s = num<T>::half_pi() * F::template eval<T, false>(x0, p);
-    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {
-        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
-        for (int r = tid; r < m; r += blockDim.x) {
-            const Node<T> nd = ldg_node(a.grid + c0 + r);
-            const T d = dx * nd.x;
-            const T xm = x0 - d, xp = x0 + d;
-            rows[r] = nd.w * (F::template eval<T, false>(xm, p) + F::template eval<T, false>(xp, p));
-        }
-        ordered_add_tile(s, rows, m);
-    }
-    if (tid == 0) a.value[b] = dx * a.h * s;
+    if (adder) s = num<T>::half_pi() * F::template eval<T, false>(x0, p);
+    ordered_sum_cluster(s, (long long)a.n, a.level, [&](long long pos) {
+        const Node<T> nd = ldg_node(a.grid + pos);
+        const T d = dx * nd.x;
+        const T xm = x0 - d, xp = x0 + d;
+        return nd.w * (F::template eval<T, false>(xm, p) + F::template eval<T, false>(xp, p));
+    });
+    if (adder) a.value[b] = dx * a.h * s;
 }
 
+// integrate2D: n axis terms, then n row terms w_i * (inner sum over j)
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord(const Args<T> a)
 {
-    __shared__ T rows[ORD_ROWS];
-    const long long b = blockIdx.x;
-    const int tid = threadIdx.x;
+    const long long b = cluster_id_x();
+    const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, b);
     const T half = num<T>::half();
@@ -1171,42 +1157,34 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord
     const T w02 = w0 * w0;
     const int n = a.n;
     T s = num<T>::zero();
-    if (tid == 0) s = w02 * F::template eval<T, false>(x0, y0, p);
-    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {  // axis terms
-        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
-        for (int r = tid; r < m; r += blockDim.x) {
-            const Node<T> nd = ldg_node(a.grid + c0 + r);
+    if (adder) s = w02 * F::template eval<T, false>(x0, y0, p);
+    ordered_sum_cluster(s, 2LL * n, a.level, [&](long long pos) {
+        if (pos < n) {
+            const Node<T> nd = ldg_node(a.grid + pos);
             const T xkp = dx * nd.x + x0, xkm = x0 - dx * nd.x;
             const T ykp = dy * nd.x + y0, ykm = y0 - dy * nd.x;
-            rows[r] = nd.w * w0 * (F::template eval<T, false>(xkp, y0, p) + F::template eval<T, false>(xkm, y0, p) +
-                                   F::template eval<T, false>(x0, ykp, p) + F::template eval<T, false>(x0, ykm, p));
+            return nd.w * w0 * (F::template eval<T, false>(xkp, y0, p) + F::template eval<T, false>(xkm, y0, p) +
+                                F::template eval<T, false>(x0, ykp, p) + F::template eval<T, false>(x0, ykm, p));
         }
-        ordered_add_tile(s, rows, m);
-    }
-    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {  // quadrant rows
-        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
-        for (int r = tid; r < m; r += blockDim.x) {
-            const Node<T> ni = ldg_node(a.grid + c0 + r);
-            const T xip = dx * ni.x + x0, xim = x0 - dx * ni.x;
-            T inner = num<T>::zero();
-            for (int j = 0; j < n; ++j) {
-                const Node<T> nj = ldg_node(a.grid + j);
-                const T yjp = dy * nj.x + y0, yjm = y0 - dy * nj.x;
-                inner = inner + nj.w * (F::template eval<T, false>(xim, yjm, p) + F::template eval<T, false>(xip, yjm, p) +
-                                        F::template eval<T, false>(xim, yjp, p) + F::template eval<T, false>(xip, yjp, p));
-            }
-            rows[r] = ni.w * inner;
+        const Node<T> ni = ldg_node(a.grid + (pos - n));
+        const T xip = dx * ni.x + x0, xim = x0 - dx * ni.x;
+        T inner = num<T>::zero();
+        for (int j = 0; j < n; ++j) {
+            const Node<T> nj = ldg_node(a.grid + j);
+            const T yjp = dy * nj.x + y0, yjm = y0 - dy * nj.x;
+            inner = inner + nj.w * (F::template eval<T, false>(xim, yjm, p) + F::template eval<T, false>(xip, yjm, p) +
+                                    F::template eval<T, false>(xim, yjp, p) + F::template eval<T, false>(xip, yjp, p));
         }
-        ordered_add_tile(s, rows, m);
-    }
-    if (tid == 0) a.value[b] = dx * dy * (a.h * a.h) * s;
+        return ni.w * inner;
+    });
+    if (adder) a.value[b] = dx * dy * (a.h * a.h) * s;
 }
 
+// integrate3D: n axis terms, then for every (i, j) its plane term followed by its octant row sum
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed3d_ord(const Args<T> a)
 {
-    __shared__ T rows[2 * ORD_ROWS];  // (plane term, octant term) per (i, j)
-    const long long b = blockIdx.x;
-    const int tid = threadIdx.x;
+    const long long b = cluster_id_x();
+    const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, b);
     const T half = num<T>::half();
@@ -1221,47 +1199,40 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_fixed3d_ord
     const int n = a.n;
 #define FE(X, Y, Z) F::template eval<T, false>(X, Y, Z, p)
     T total = num<T>::zero();
-    if (tid == 0) total = w03 * FE(x0, y0, z0);
-    for (int c0 = 0; c0 < n; c0 += ORD_ROWS) {  // axis terms
-        const int m = n - c0 < ORD_ROWS ? n - c0 : ORD_ROWS;
-        for (int r = tid; r < m; r += blockDim.x) {
-            const Node<T> nd = ldg_node(a.grid + c0 + r);
+    if (adder) total = w03 * FE(x0, y0, z0);
+    ordered_sum_cluster(total, (long long)n + 2LL * n * n, a.level, [&](long long pos) {
+        if (pos < n) {
+            const Node<T> nd = ldg_node(a.grid + pos);
             const T axis = (FE(dx * nd.x + x0, y0, z0) + FE(x0 - dx * nd.x, y0, z0)) + (FE(x0, dy * nd.x + y0, z0) + FE(x0, y0 - dy * nd.x, z0)) +
                            (FE(x0, y0, dz * nd.x + z0) + FE(x0, y0, z0 - dz * nd.x));
-            rows[r] = nd.w * w02 * axis;
+            return nd.w * w02 * axis;
         }
-        ordered_add_tile(total, rows, m);
-    }
-    const long long npair = (long long)n * n;
-    for (long long c0 = 0; c0 < npair; c0 += ORD_ROWS) {  // (i, j) rows: plane term, then the octant row sum
-        const int m = (int)(npair - c0 < ORD_ROWS ? npair - c0 : ORD_ROWS);
-        for (int r = tid; r < m; r += blockDim.x) {
-            const long long q = c0 + r;
-            const int i = (int)(q / n), j = (int)(q - (long long)i * n);
-            const Node<T> ni = ldg_node(a.grid + i);
-            const T xp = dx * ni.x + x0, xm = x0 - dx * ni.x;
+        const long long q = (pos - n) >> 1;
+        const int i = (int)(q / n), j = (int)(q - (long long)i * n);
+        const Node<T> ni = ldg_node(a.grid + i);
+        const T xp = dx * ni.x + x0, xm = x0 - dx * ni.x;
+        const Node<T> nj = ldg_node(a.grid + j);
+        const T wiwj = ni.w * nj.w;
+        const T yp = dy * nj.x + y0, ym = y0 - dy * nj.x;
+        if (((pos - n) & 1) == 0) {
             const T ypi = dy * ni.x + y0, ymi = y0 - dy * ni.x;
-            const Node<T> nj = ldg_node(a.grid + j);
-            const T wiwj = ni.w * nj.w;
-            const T yp = dy * nj.x + y0, ym = y0 - dy * nj.x;
             const T zpj = dz * nj.x + z0, zmj = z0 - dz * nj.x;
             const T plane = (FE(xp, yp, z0) + FE(xm, yp, z0) + FE(xp, ym, z0) + FE(xm, ym, z0)) +
                             (FE(xp, y0, zpj) + FE(xm, y0, zpj) + FE(xp, y0, zmj) + FE(xm, y0, zmj)) +
                             (FE(x0, ypi, zpj) + FE(x0, ymi, zpj) + FE(x0, ypi, zmj) + FE(x0, ymi, zmj));
-            rows[2 * r] = wiwj * w0 * plane;
-            T oct = num<T>::zero();
-            for (int k = 0; k < n; ++k) {
-                const Node<T> nk = ldg_node(a.grid + k);
-                const T zp = dz * nk.x + z0, zm = z0 - dz * nk.x;
-                oct = oct + nk.w * ((FE(xp, yp, zp) + FE(xm, yp, zp) + FE(xp, ym, zp) + FE(xm, ym, zp)) +
-                                    (FE(xp, yp, zm) + FE(xm, yp, zm) + FE(xp, ym, zm) + FE(xm, ym, zm)));
-            }
-            rows[2 * r + 1] = wiwj * oct;
+            return wiwj * w0 * plane;
         }
-        ordered_add_tile(total, rows, 2 * m);
-    }
+        T oct = num<T>::zero();
+        for (int k = 0; k < n; ++k) {
+            const Node<T> nk = ldg_node(a.grid + k);
+            const T zp = dz * nk.x + z0, zm = z0 - dz * nk.x;
+            oct = oct + nk.w * ((FE(xp, yp, zp) + FE(xm, yp, zp) + FE(xp, ym, zp) + FE(xm, ym, zp)) +
+                                (FE(xp, yp, zm) + FE(xm, yp, zm) + FE(xp, ym, zm) + FE(xm, ym, zm)));
+        }
+        return wiwj * oct;
+    });
 #undef FE
-    if (tid == 0) a.value[b] = (dx * dy * dz * (a.h * a.h * a.h)) * total;
+    if (adder) a.value[b] = (dx * dy * dz * (a.h * a.h * a.h)) * total;
 }
 
 }  // namespace fts
