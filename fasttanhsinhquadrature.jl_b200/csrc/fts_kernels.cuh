@@ -468,6 +468,32 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
 }
 
+// s += terms[0] + terms[1] + ... in index order, one thread.  The chain of dependent adds is the
+// whole cost, so the loads run eight terms ahead of it (a plain loop exposes the shared-memory
+// latency once per unrolled group: 15-20 cycles per term instead of the add's 8).
+template <class T> __device__ __forceinline__ void ordered_add(T& s, const T* terms, int m)
+{
+    T cur[8];
+    int i = 0;
+    if (m >= 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = terms[k];
+        for (; i + 16 <= m; i += 8) {
+            T nxt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nxt[k] = terms[i + 8 + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = s + cur[k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = s + cur[k];
+        i += 8;
+    }
+    for (; i < m; ++i) s = s + terms[i];
+}
+
 // Deep levels of queued 1D integrals (see Args::tail_level): one CTA per integral.  The CTA
 // evaluates a tile of w_i*(f(x+)+f(x-)) terms in parallel into shared memory, then ONE thread adds
 // them in index order, so the result is bit-identical to the sequential reference loop
@@ -533,7 +559,7 @@ template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bound
                     }
                     if (tid == 0) s_new = s_new + terms[0];
                 } else if (tid == 0) {
-                    for (int i = 0; i < m; ++i) s_new = s_new + terms[i];
+                    ordered_add(s_new, terms, m);
                 }
                 __syncthreads();
             }
@@ -828,32 +854,6 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
 // the same device function the thread-per-integral kernel calls), and one thread adds the tile in
 // order.  Bit-identical to k_adaptive{2,3}d_tpi<.., false>; the dependent add (8 cycles per term)
 // replaces a dependent chain of whole integrand evaluations, ~20-50x faster for one integral.
-
-// s += terms[0] + terms[1] + ... in index order, one thread.  The chain of dependent adds is the
-// whole cost, so the loads run eight terms ahead of it (a plain loop exposes the shared-memory
-// latency once per unrolled group: 15-20 cycles per term instead of the add's 8).
-template <class T> __device__ __forceinline__ void ordered_add(T& s, const T* terms, int m)
-{
-    T cur[8];
-    int i = 0;
-    if (m >= 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cur[k] = terms[k];
-        for (; i + 16 <= m; i += 8) {
-            T nxt[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) nxt[k] = terms[i + 8 + k];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s = s + cur[k];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s = s + cur[k];
-        i += 8;
-    }
-    for (; i < m; ++i) s = s + terms[i];
-}
 
 // ---- thread-block cluster plumbing of the ordered adaptive kernels ------------------------------
 // One integral may be served by a CLUSTER of up to 8 CTAs: every CTA evaluates terms and stores them
