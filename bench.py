@@ -321,7 +321,7 @@ def main():
     if not args.no_cpu_baseline:
         try:
             cpu = cpu_reference(args.batch_log2, steps=5, warmup=1, sample_log2=args.batch_log2, bounded=True)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "gevals_per_s")}
+            cpu = {k: cpu[k] for k in ("value", "value_1core", "unit", "cores", "kind", "sample", "gevals_per_s")}
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
     line = {"metric": METRIC, "value": value_ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
