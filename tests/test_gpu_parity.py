@@ -666,6 +666,16 @@ def test_nvrtc_integrand_equals_builtin(gpu):
     x, w, h = gpu.tanhsinh(np.float64, 64)
     u3 = gpu.cuda_integrand("return fts::fm::exp(x + y + z);", "3d")
     assert gpu.integrate3D_avx(u3, x, w, h) == gpu.integrate3D_avx(gpu.builtin("exp_3d"), x, w, h)
+    # reference order on ONE box: the cluster-launched ordered kernels, NVRTC module vs static kernel
+    assert gpu.integrate3D(u3, x, w, h, order="reference") == gpu.integrate3D(gpu.builtin("exp_3d"), x, w, h, order="reference")
+    c3 = gpu.adaptive_cache_3D(np.float64, max_levels=4)
+    assert (gpu.adaptive_integrate_3D(np.float64, u3, [-1.0] * 3, [1.0, 2.0, 1.5], rtol=1e-9, max_levels=4, cache=c3, order="reference")
+            == gpu.adaptive_integrate_3D(np.float64, gpu.builtin("exp_3d"), [-1.0] * 3, [1.0, 2.0, 1.5], rtol=1e-9, max_levels=4, cache=c3,
+                                         order="reference"))
+    u2 = gpu.cuda_integrand("return fts::fm::exp(x + y);", "2d")
+    c2 = gpu.adaptive_cache_2D(np.float64, max_levels=6)
+    assert (gpu.quad(u2, [-1.0, 0.0], [1.0, 2.0], rtol=1e-10, max_levels=6, cache=c2, order="reference")
+            == gpu.quad(gpu.builtin("exp_2d"), [-1.0, 0.0], [1.0, 2.0], rtol=1e-10, max_levels=6, cache=c2, order="reference"))
     # something no builtin family covers: cos(pi x)/sqrt(1-x) written with the complement distance
     uc = gpu.cuda_integrand("return cos(T(3.141592653589793) * x) / sqrt(bmx);", "cmpl")
     v = gpu.quad_cmpl(uc, -1.0, 1.0, rtol=1e-12)
