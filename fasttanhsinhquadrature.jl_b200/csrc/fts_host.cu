@@ -709,7 +709,7 @@ static int tpi_block(int dim, int dtype)
     static const int pinned = [] {
         const char* e = getenv("FTS_B200_TPI_BLOCK");
         const int v = e ? atoi(e) : 0;
-        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 0;
+        return (v >= 32 && v <= 256 && v % 32 == 0) ? v : 0;
     }();
     if (dim != 1) return 128;
     if (pinned) return pinned;
