@@ -810,3 +810,74 @@ def test_every_builtin_family_agrees_across_orders(gpu):
             # where the level differs the two estimates still agree to the requested tolerance
             if (~same).any():
                 assert rel(rf.value[~same], rr.value[~same]).max() <= 50 * rt, (name, T)
+
+
+# ------------------------------------------------------------------ the reference's KATs ------
+def test_reference_kats_on_the_gpu(gpu, oracle):
+    """The analytic known-answer tests of /root/reference/test/*.jl (the list pinned on the oracle in
+    tests/test_oracle_golden.py), run through the GPU path in BOTH summation orders, and compared
+    with the oracle's value of the same call (reference order: <= 1e-14 relative, same stop level)."""
+    e1 = math.e - 1 / math.e
+    for order in ("reference", "fast"):
+        # fixed grids 1D: test/families_1d.jl:12-16 (N=120), runtests.jl:101-110 (N=80), dispatch.jl:36
+        x, w, h = gpu.tanhsinh(np.float64, 120)
+        assert abs(gpu.integrate1D(gpu.builtin("poly6"), x, w, h, order=order) - 9 / 7) < 1e-12
+        assert abs(gpu.integrate1D(gpu.builtin("runge"), x, w, h, params=[25.0], order=order) - 2 * math.atan(5.0) / 5) < 1e-6
+        assert abs(gpu.integrate1D(gpu.builtin("exp"), x, w, h, order=order) - e1) < 1e-12
+        assert abs(gpu.integrate1D(gpu.builtin("log1mx"), x, w, h, order=order) - (2 * math.log(2) - 2)) < 1e-11
+        x, w, h = gpu.tanhsinh(np.float64, 80)
+        for coeffs in ([1.0] + [0.0] * 7, [1.0, 1.0] + [0.0] * 6, [0, 0, 3.0] + [0.0] * 5):
+            assert abs(gpu.integrate1D(gpu.builtin("poly7"), x, w, h, params=coeffs, order=order) - 2.0) < 1e-12
+        assert abs(gpu.integrate1D(gpu.builtin("exp"), 0.0, 1.0, x, w, h, order=order) - (math.e - 1)) < 1e-13       # README.md:174-181
+        assert abs(gpu.integrate1D(gpu.builtin("sin2"), 0.0, PI, x, w, h, params=[1.0], order=order) - PI / 2) < 1e-12
+        # fixed grids 2D/3D: families_2d.jl:5-8,16-23,32,37-44; families_3d.jl:1-22 (N=60), 24-49 (N=80)
+        p2 = gpu.builtin("poly2_2d")
+        assert abs(gpu.integrate2D(p2, x, w, h, params=[1, 0, 0, 1, 0, 1], order=order) - 20 / 3) < 1e-12
+        a, b, c, d = -2.0, 3.0, -1.0, 2.0
+        exact = ((b ** 3 - a ** 3) / 3) * (d - c) + ((d ** 2 - c ** 2) / 2) * (b - a)
+        assert abs(gpu.integrate2D(p2, [a, c], [b, d], x, w, h, params=[0, 0, 1, 1, 0, 0], order=order) - exact) < 1e-11
+        assert abs(gpu.integrate2D(p2, [1.0, -1.0], [0.0, 2.0], x, w, h, params=[1, 0, 0, 0, 0, 0], order=order) + 3.0) < 1e-12
+        x6, w6, h6 = gpu.tanhsinh(np.float64, 60)
+        p3 = gpu.builtin("poly2_3d")
+        assert abs(gpu.integrate3D(p3, x6, w6, h6, params=[1, 0, 0, 0, 0, 0], order=order) - 8) < 1e-12
+        assert abs(gpu.integrate3D(p3, x6, w6, h6, params=[0, 0, 0, 0, 1, 0], order=order)) < 1e-14
+        assert abs(gpu.integrate3D(gpu.builtin("x2y2z2"), x6, w6, h6, order=order) - 8 / 27) < 1e-13
+        low, up = [-2.0, -1.0, 0.0], [3.0, 2.0, 4.0]
+        mono = lambda lo_, hi_, q: (hi_ ** (q + 1) - lo_ ** (q + 1)) / (q + 1)
+        vol = lambda px, py, pz: mono(low[0], up[0], px) * mono(low[1], up[1], py) * mono(low[2], up[2], pz)
+        assert abs(gpu.integrate3D(p3, low, up, x, w, h, params=[0, 1, 2, 3, 0, 0], order=order) - (vol(2, 0, 0) + 2 * vol(0, 1, 0) + 3 * vol(0, 0, 2))) < 1e-10
+        # adaptive 1D: families_1d.jl:22-26, runtests.jl:205-208, families_1d.jl:48-51
+        c1 = gpu.adaptive_cache_1D(np.float64, max_levels=16)
+        for name, par, exact, tol in (("poly6", None, 9 / 7, 1e-12), ("runge", [25.0], 2 * math.atan(5.0) / 5, 1e-12), ("exp", None, e1, 1e-12),
+                                      ("log1mx", None, 2 * math.log(2) - 2, 1e-11)):
+            r = gpu.adaptive_integrate_1D(np.float64, gpu.builtin(name), -1.0, 1.0, rtol=1e-12, cache=c1, params=par, order=order, full_output=True)
+            assert r.converged[0] and abs(r.value[0] - exact) < tol, (name, order)
+        assert abs(gpu.adaptive_integrate_1D(np.float64, gpu.builtin("exp"), 0.0, 1.0, rtol=1e-8, cache=c1, order=order) - (math.e - 1)) < 1e-8
+        assert abs(gpu.adaptive_integrate_1D(np.float64, gpu.builtin("sin2"), -PI, PI, cache=c1, params=[1000.0], order=order) - PI) < 1e-10
+        # complement: families_1d.jl:26,32-44; runtests.jl:416-425
+        cc = gpu.adaptive_cache_1D(np.float64, max_levels=20, complement=True)
+        for lo_, up_ in ((-1.0, 1.0), (-2.5, 3.25)):
+            assert abs(gpu.adaptive_integrate_1D_cmpl(np.float64, gpu.builtin("c_invsqrt"), lo_, up_, rtol=1e-12, cache=cc, params=[1.0], order=order) - PI) < 1e-12
+        for name in ("c_log_bmx", "c_log_xma"):
+            v = gpu.adaptive_integrate_1D_cmpl(np.float64, gpu.builtin(name), -2.5, 3.25, rtol=1e-12, cache=cc, order=order)
+            assert abs(v - 5.75 * (math.log(5.75) - 1)) < 1e-12
+        v = gpu.adaptive_integrate_1D_cmpl(np.float64, gpu.builtin("c_exp_inv_bmx"), 0.0, 1.0, rtol=1e-14, max_levels=20, cache=cc, order=order)
+        assert abs(v - 0.1484955067759220479) < 1e-14
+        # adaptive 3D: families_3d.jl:51-70
+        c3 = gpu.adaptive_cache_3D(np.float64, max_levels=5)
+        assert abs(gpu.adaptive_integrate_3D(np.float64, gpu.builtin("exp_3d"), [-1.0] * 3, [1.0] * 3, rtol=1e-9, cache=c3, order=order) - e1 ** 3) < 1e-9
+        exact_rat = (2 * math.atan(5.0) / 5) * (2 * math.atan(4.0) / 4) * (2 * math.atan(3.0) / 3)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert abs(gpu.adaptive_integrate_3D(np.float64, gpu.builtin("rat_3d"), [-1.0] * 3, [1.0] * 3, rtol=1e-6, cache=c3, order=order) - exact_rat) < 1e-6
+    # reference order against the oracle, value for value
+    c1o, c3o = oracle.cache1d("f64", 16), oracle.cache_tensor("f64", 3, 5)
+    for name, fam, par in (("poly6", F["F1_POLY6"], None), ("runge", F["F1_RUNGE"], [25.0]), ("exp", F["F1_EXP"], None), ("log1mx", F["F1_LOG1MX"], None)):
+        r = gpu.adaptive_integrate_1D(np.float64, gpu.builtin(name), -1.0, 1.0, rtol=1e-12, cache=gpu.adaptive_cache_1D(np.float64, max_levels=16), params=par,
+                                      order="reference", full_output=True)
+        ro = oracle.adaptive1d("f64", fam, par, -1.0, 1.0, 1e-12, 0.0, 16, c1o)
+        assert r.levels[0] == ro.level and rel(r.value[0], ro.value) <= RTOL64, name
+    r = gpu.adaptive_integrate_3D(np.float64, gpu.builtin("exp_3d"), [-1.0] * 3, [1.0] * 3, rtol=1e-9, cache=gpu.adaptive_cache_3D(np.float64, max_levels=5),
+                                  order="reference", full_output=True)
+    ro = oracle.adaptive_nd("f64", 3, F["F3_EXP"], None, [-1.0] * 3, [1.0] * 3, 1e-9, 0.0, 5, c3o)
+    assert r.levels[0] == ro.level and rel(r.value[0], ro.value) <= RTOL64 and int(gpu.evals_for_level(3, r.levels)[0]) == ro.evals
