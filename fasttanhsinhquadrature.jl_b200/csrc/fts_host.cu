@@ -38,6 +38,7 @@ cudaDeviceProp g_prop;
 cudaStream_t g_stream = nullptr;  // internal stream of the host-buffer entry points
 cudaStream_t g_pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of fts_adaptive_batch
 cudaEvent_t g_pipe_ev = nullptr;
+unsigned long long* g_peer_wait = nullptr;  // [64] device: per-level exchange wait of the last fused sharded call (ns)
 
 std::vector<KernelEntry>& registry()
 {
@@ -138,6 +139,8 @@ const FamilyInfo* family_info(int family)
 }
 }  // namespace fts_host
 
+static void drop_device_state();  // per-stream queues and other device buffers owned by the library
+
 static int ensure_init()
 {
     if (g_inited) return FTS_OK;
@@ -179,6 +182,7 @@ extern "C" int fts_init(int device)
     if (g_inited && g_device != device) {
         // re-binding: drop per-device scratch
         for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+        drop_device_state();
         if (g_stream) cudaStreamDestroy(g_stream);
         for (auto& ps : g_pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
         if (g_pipe_ev) cudaEventDestroy(g_pipe_ev);
@@ -209,6 +213,7 @@ extern "C" int fts_shutdown(void)
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return FTS_OK;
     for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+    drop_device_state();
     if (g_stream) cudaStreamDestroy(g_stream);
     for (auto& ps : g_pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
     if (g_pipe_ev) cudaEventDestroy(g_pipe_ev);
@@ -978,11 +983,26 @@ static int tail_queue_for(cudaStream_t s, size_t batch, int** out)
         }
         const size_t cap = batch + batch / 4 + 1024;
         FTS_CUDA(cudaMalloc((void**)&q->buf, sizeof(int) * (cap + 2)));
-        FTS_CUDA(cudaMemset(q->buf, 0, sizeof(int) * 2));
+        FTS_CUDA(cudaMemsetAsync(q->buf, 0, sizeof(int) * 2, s));  // ordered before the first kernel on `s` (non-blocking streams do not wait for the legacy stream)
         q->cap = cap;
     }
     *out = q->buf;
     return FTS_OK;
+}
+
+// fts_shutdown / re-binding to another device: the queues are keyed by raw stream pointers, which a
+// later stream (possibly on another device) may reuse, and their buffers belong to the old device
+static void drop_device_state()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_tail_mu);
+        for (auto& e : g_tail_queues)
+            if (e.second.buf) cudaFree(e.second.buf);
+        g_tail_queues.clear();
+    }
+    if (g_peer_wait) cudaFree(g_peer_wait);
+    g_peer_wait = nullptr;
+    cudaGetLastError();
 }
 
 // kernel style an adaptive launch will use (shared by run_adaptive and the host-buffer entry point)
@@ -1295,6 +1315,26 @@ extern "C" int fts_peer_mailbox_bytes(int nranks, size_t* bytes)
     return FTS_OK;
 }
 
+// per-level exchange wait of the last fused call (ns, written by k_sharded_step_fused), and the
+// spin timeout of that kernel
+static unsigned long long peer_timeout_ns()
+{
+    static const unsigned long long v = [] {
+        const char* e = getenv("FTS_B200_PEER_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 10000;
+        return (unsigned long long)(ms < 1 ? 1 : ms) * 1000000ULL;
+    }();
+    return v;
+}
+
+extern "C" int fts_peer_wait_ns(int nlevels, uint64_t* out)
+{
+    if (nlevels < 0 || nlevels > 64 || !out) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_peer_wait_ns: 0 <= nlevels <= 64 and a buffer");
+    if (!g_peer_wait) { memset(out, 0, sizeof(uint64_t) * nlevels); return FTS_OK; }
+    FTS_CUDA(cudaMemcpy(out, g_peer_wait, sizeof(uint64_t) * nlevels, cudaMemcpyDeviceToHost));
+    return FTS_OK;
+}
+
 template <class T>
 static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up, const T* params, T rtol, T atol, int max_levels,
                          int shard_from, int rank, int nranks, void* const* mailboxes, double epoch, T* state, int options, cudaStream_t s)
@@ -1309,6 +1349,11 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
     T* partial = scratch + 2 * nblk;
     unsigned int* ticket = (unsigned int*)(partial + 2);
     FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    if (!g_peer_wait) {
+        FTS_CUDA(cudaMalloc((void**)&g_peer_wait, 64 * sizeof(unsigned long long)));
+        FTS_CUDA(cudaMemsetAsync(g_peer_wait, 0, 64 * sizeof(unsigned long long), s));
+    }
+    const unsigned long long tmo = peer_timeout_ns();
     const T tm = load_elem<T>(c->tm);
     const int parity = ((long long)epoch) & 1;
     for (int level = 0; level <= max_levels; ++level) {
@@ -1326,8 +1371,8 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
         }
         if (int rc = launch_raw(fn, grid_level_blocks(dim, level, a.nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s)) return rc;
         if (shard) {
-            if (dim == 3) fts::k_sharded_step_fused<T, 3><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options);
-            else fts::k_sharded_step_fused<T, 2><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options);
+            if (dim == 3) fts::k_sharded_step_fused<T, 3><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait);
+            else fts::k_sharded_step_fused<T, 2><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait);
             g_launches.fetch_add(1);
         } else {
             if (dim == 3) launch_step<T, 3>(low, up, tm, rtol, atol, level, 1, partial, state, s, options);

@@ -882,11 +882,22 @@ __device__ __forceinline__ unsigned cluster_map(const void* p, unsigned rank)
 }
 __device__ __forceinline__ void cluster_store(unsigned addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 __device__ __forceinline__ void cluster_store(unsigned addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ int cluster_load_int(unsigned addr)
+__device__ __forceinline__ void cluster_store_int(unsigned addr, int v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// Distributed-shared-memory lifetime rules the ordered kernels keep:
+//  (1) no CTA touches a peer's shared memory before cluster_entry_sync() — until then the peer may
+//      not have started;
+//  (2) nobody READS remote shared memory at all: the adder pushes the stop flag into every CTA's own
+//      s_done before the level's closing barrier, so after the last barrier a CTA only looks at its
+//      own memory and CTA 0 may retire while its peers are still leaving.
+__device__ __forceinline__ void cluster_entry_sync()
 {
-    int v;
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
+    if (cluster_nctarank() > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// adder thread: publish `v` to the s_done word of every CTA of the cluster (own CTA included)
+__device__ __forceinline__ void cluster_broadcast_int(int* local_word, int v)
+{
+    const unsigned csize = cluster_nctarank();
+    for (unsigned r = 0; r < csize; ++r) cluster_store_int(cluster_map(local_word, r), v);
 }
 
 // Ordered sum of term(0), term(1), ..., term(nterms-1) into s (valid in the adder thread: thread 0 of
@@ -959,7 +970,6 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive2d_
     __shared__ int s_done;
     const long long b = cluster_id_x();  // one integral per cluster (of 1, 2, 4 or 8 CTAs)
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
-    const unsigned done_remote = cluster_map(&s_done, 0);
     const int tid = adder ? 0 : 1;  // "thread 0" below = the adder thread of the cluster
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, b);
@@ -968,8 +978,9 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive2d_
     int flags;
     if (!load_box<2>(a, b, lo, hi, neg, flags)) {
         if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
-        return;
+        return;  // the whole cluster leaves (same box in every CTA), nothing remote was touched
     }
+    cluster_entry_sync();
     const T half = num<T>::half();
     Box2<T> bx;
     bx.dx = half * (hi[0] - lo[0]); bx.x0 = half * (hi[0] + lo[0]);
@@ -1009,10 +1020,10 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive2d_
             old_res = new_res;
             const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
             if (conv) flags |= FLAG_CONVERGED;
-            s_done = conv ? 1 : 0;
+            cluster_broadcast_int(&s_done, conv ? 1 : 0);
         }
         cluster_sync();
-        if (cluster_load_int(done_remote)) break;
+        if (*(volatile int*)&s_done) break;
     }
     if (tid == 0) {
         if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
@@ -1068,7 +1079,6 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
     __shared__ int s_done;
     const long long b = cluster_id_x();  // one integral per cluster (of 1, 2, 4 or 8 CTAs)
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
-    const unsigned done_remote = cluster_map(&s_done, 0);
     const int tid = adder ? 0 : 1;  // "thread 0" below = the adder thread of the cluster
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, b);
@@ -1077,8 +1087,9 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
     int flags;
     if (!load_box<3>(a, b, lo, hi, neg, flags)) {
         if (tid == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
-        return;
+        return;  // the whole cluster leaves (same box in every CTA), nothing remote was touched
     }
+    cluster_entry_sync();
     const T half = num<T>::half();
     const Box3<T> bx = make_box3(lo, hi);
     T h = a.tm * half;
@@ -1101,10 +1112,10 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
             old_res = new_res;
             const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
             if (conv) flags |= FLAG_CONVERGED;
-            s_done = conv ? 1 : 0;
+            cluster_broadcast_int(&s_done, conv ? 1 : 0);
         }
         cluster_sync();
-        if (cluster_load_int(done_remote)) break;
+        if (*(volatile int*)&s_done) break;
     }
     if (tid == 0) {
         if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
@@ -1123,6 +1134,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
 // (cluster machinery of ordered_sum_cluster: one cluster of 1..8 CTAs per integral)
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed1d_ord(const Args<T> a)
 {
+    cluster_entry_sync();
     const long long b = cluster_id_x();
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
     T p[F::NP > 0 ? F::NP : 1];
@@ -1144,6 +1156,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_fixed1d_ord
 // integrate2D: n axis terms, then n row terms w_i * (inner sum over j)
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord(const Args<T> a)
 {
+    cluster_entry_sync();
     const long long b = cluster_id_x();
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
     T p[F::NP > 0 ? F::NP : 1];
@@ -1183,6 +1196,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord
 // integrate3D: n axis terms, then for every (i, j) its plane term followed by its octant row sum
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed3d_ord(const Args<T> a)
 {
+    cluster_entry_sync();
     const long long b = cluster_id_x();
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
     T p[F::NP > 0 ? F::NP : 1];

@@ -814,27 +814,44 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
 
 // Stop test of the fused path: lane r of one warp waits for rank r's flag in OUR mailbox (peers
 // write it through NVLink), then thread 0 does the arithmetic of k_sharded_step.  A rank that never
-// arrives trips a 2 s timeout -> state[5] = 3 and every later launch of the call exits.
+// arrives trips the timeout (FTS_B200_PEER_TIMEOUT_MS, default 10 s: host-side skew between ranks —
+// first-call module loads, a garbage collection — must not look like a dead peer) -> state[5] = 3 and
+// every later launch of the call exits.
 template <class T, int D> __global__ void k_sharded_step_fused(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
-                                                               const double* mail, int mail_slot, double epoch, T* state, int options)
+                                                               const double* mail, int mail_slot, double epoch, T* state, int options,
+                                                               unsigned long long timeout_ns, unsigned long long* wait_ns)
 {
     __shared__ int s_ok;
-    if (level > 0 && state[5] != num<T>::zero()) return;
+    if (level > 0 && state[5] != num<T>::zero()) {
+        if (wait_ns && threadIdx.x == 0) wait_ns[level] = 0ULL;
+        return;
+    }
     const int lane = threadIdx.x;
     if (lane == 0) s_ok = 1;
     __syncwarp();
+    unsigned long long waited = 0ULL;
     if (lane < nranks) {
         const volatile double* slot = mail + ((size_t)mail_slot * nranks + lane) * 4;
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        t1 = t0;
         while (slot[2] != epoch) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 2000000000ULL) {
+            if (t1 - t0 > timeout_ns) {
                 s_ok = 0;
                 break;
             }
         }
+        waited = t1 - t0;
     }
+    // time this rank spent waiting for the slowest peer's flag (0 when every flag was already there):
+    // the per-level exchange wait bench.py reports for the sharded 3D integral
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, waited, off);
+        waited = o > waited ? o : waited;
+    }
+    if (wait_ns && lane == 0) wait_ns[level] = waited;
     __syncwarp();
     __threadfence_system();
     if (lane != 0) return;

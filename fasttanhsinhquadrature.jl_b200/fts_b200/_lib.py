@@ -93,6 +93,7 @@ _SIGS = {
     "fts_peer_close": (ci, [vp]),
     "fts_peer_free": (ci, [vp]),
     "fts_adaptive_sharded_fused_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp), C.c_uint64, vp, vp]),
+    "fts_peer_wait_ns": (ci, [ci, C.POINTER(C.c_uint64)]),
     "fts_integrand_cubin_size": (ci, [vp, C.POINTER(cs_), C.POINTER(ci)]),
     "fts_measure_fma_peak": (ci, [ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fts_launch_count": (i64, [ci]),

@@ -152,6 +152,98 @@ class PeerMailboxes:
         return cls._cache[key]
 
 
+class ShardedPlan:
+    """Device buffers and launch closure of ONE sharded 2D/3D integral, so that a caller (bench.py)
+    can queue the same integral repeatedly between CUDA events without host work in between.
+    `launch()` queues every level on torch's current stream and returns immediately; `result()`
+    synchronises and reads the 8-element state."""
+
+    def __init__(self, T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
+                 shard_from_level: Optional[int] = None, exchange: str = "peer", world: Optional[int] = None, rank: Optional[int] = None):
+        import torch
+        dist = _dist()
+        self.dt = dt = api._dt(T)
+        if dt == api.Double64:
+            raise api.FtsError(L.ERR_UNSUPPORTED, "sharded integrals: float32/float64")
+        # world/rank may be forced to 1/0: every rank then computes the WHOLE integral without any
+        # exchange (the N = 1 arm of a strong-scaling measurement, run on all GPUs at once)
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.group, self.f, self.exchange, self.max_levels = group, f, exchange, max_levels
+        self.rtol_T, self.atol_T = api._resolve_tolerances(dt, rtol, atol)
+        self.dim = f.dim
+        if cache is None:
+            cache = api.adaptive_cache_3D(dt, max_levels=max_levels) if self.dim == 3 else api.adaptive_cache_2D(dt, max_levels=max_levels)
+        else:
+            api._require_cache_levels(cache, max_levels)
+        self.cache = cache
+        tdt = torch.float32 if dt == np.dtype(np.float32) else torch.float64
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.lo = torch.tensor(np.asarray(low, dt), dtype=tdt, device=dev)
+        self.hi = torch.tensor(np.asarray(up, dt), dtype=tdt, device=dev)
+        self.p = torch.tensor(np.asarray(params, dt), dtype=tdt, device=dev) if (params is not None and f.nparams) else None
+        self.partial = torch.zeros(2, dtype=tdt, device=dev)
+        self.gathered = torch.zeros(self.world, 2, dtype=tdt, device=dev)
+        self.state = torch.zeros(8, dtype=tdt, device=dev)
+        if shard_from_level is None:
+            shard_from_level = (max_levels + 1 if exchange == "peer" else 0) if self.world == 1 else (5 if self.dim == 3 else 8)
+        self.shard_from_level = shard_from_level
+        # the mailboxes belong to the process group; a plan forced to one rank never exchanges
+        self.mb = PeerMailboxes.get(group) if (exchange == "peer" and world is None) else None
+        if self.mb is None and exchange == "peer":
+            self.shard_from_level = max_levels + 1
+
+    def launch(self) -> None:
+        import ctypes as C
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+        lo, hi, p, state, cache, f = self.lo, self.hi, self.p, self.state, self.cache, self.f
+        if self.exchange == "peer":
+            mb = self.mb
+            epoch = 1
+            if mb is not None:
+                mb.epoch += 1
+                epoch = mb.epoch
+            L.check(L.lib.fts_adaptive_sharded_fused_dev(
+                cache.handle, f._h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(p.data_ptr()) if p is not None else None,
+                api._ptr(self.rtol_T), api._ptr(self.atol_T), self.max_levels, self.shard_from_level, self.rank, self.world,
+                mb.ptrs if mb is not None else None, C.c_uint64(epoch), C.c_void_p(state.data_ptr()), C.c_void_p(stream)))
+            return
+        dist = _dist()
+        partial, gathered, world, group = self.partial, self.gathered, self.world, self.group
+
+        def level_fn(level, r, w):
+            api.sharded_level_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), params=p.data_ptr() if p is not None else 0, level=level,
+                                  rank=r, nranks=w, partial=partial.data_ptr(), state=state.data_ptr(), stream=stream)
+            return partial
+
+        def all_gather(t):
+            if world == 1:
+                gathered.copy_(t.view(1, 2))
+            else:
+                dist.all_gather_into_tensor(gathered.view(-1), t, group=group)
+            return gathered
+
+        def step_fn(level, parts):
+            api.sharded_step_dev(cache, low=lo.data_ptr(), up=hi.data_ptr(), rtol=self.rtol_T[0], atol=self.atol_T[0], level=level, nranks=parts.shape[0],
+                                 partials=parts.data_ptr(), state=state.data_ptr(), stream=stream)
+
+        run_sharded_levels(self.max_levels, self.rank, world, level_fn, step_fn, all_gather, self.shard_from_level)
+
+    def result(self):
+        s = self.state.cpu().numpy()  # the only host synchronisation
+        if s[5] == 3:
+            raise api.FtsError(L.ERR_CUDA, "sharded integral: a rank did not deliver its level partial in time (peer exchange timed out, FTS_B200_PEER_TIMEOUT_MS)")
+        return s
+
+    def exchange_wait_ns(self) -> np.ndarray:
+        """per-level time this rank's stop test spent waiting for the slowest peer's flag in the last fused call"""
+        import ctypes as C
+        out = (C.c_uint64 * 64)()
+        L.check(L.lib.fts_peer_wait_ns(self.max_levels + 1, out))
+        return np.array(out[: self.max_levels + 1], dtype=np.uint64)
+
+
 def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
                                warn: bool = True, shard_from_level: Optional[int] = None, exchange: str = "peer"):
     """One large adaptive 2D/3D integral over all ranks of `group`.  Returns an AdaptiveResult
@@ -160,60 +252,11 @@ def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: 
     exchange="peer": the fused path — level kernels store their partials into every rank's
     mailbox over NVLink peer memory, the stop test waits on the device; ONE C call queues all
     levels.  exchange="nccl": level kernel -> NCCL all-gather -> stop-test kernel per level."""
-    import torch
-    dist = _dist()
-    dt = api._dt(T)
-    if dt == api.Double64:
-        raise api.FtsError(L.ERR_UNSUPPORTED, "sharded integrals: float32/float64")
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    rtol_T, atol_T = api._resolve_tolerances(dt, rtol, atol)
-    dim = f.dim
-    if cache is None:
-        cache = api.adaptive_cache_3D(dt, max_levels=max_levels) if dim == 3 else api.adaptive_cache_2D(dt, max_levels=max_levels)
-    else:
-        api._require_cache_levels(cache, max_levels)
-    tdt = torch.float32 if dt == np.dtype(np.float32) else torch.float64
-    dev = torch.device("cuda", torch.cuda.current_device())
-    lo = torch.tensor(np.asarray(low, dt), dtype=tdt, device=dev)
-    hi = torch.tensor(np.asarray(up, dt), dtype=tdt, device=dev)
-    p = torch.tensor(np.asarray(params, dt), dtype=tdt, device=dev) if (params is not None and f.nparams) else None
-    partial = torch.zeros(2, dtype=tdt, device=dev)
-    gathered = torch.zeros(world, 2, dtype=tdt, device=dev)
-    state = torch.zeros(8, dtype=tdt, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def level_fn(level, r, w):
-        api.sharded_level_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), params=p.data_ptr() if p is not None else 0, level=level,
-                              rank=r, nranks=w, partial=partial.data_ptr(), state=state.data_ptr(), stream=stream)
-        return partial
-
-    def all_gather(t):
-        if world == 1:
-            gathered.copy_(t.view(1, 2))
-        else:
-            dist.all_gather_into_tensor(gathered.view(-1), t, group=group)
-        return gathered
-
-    def step_fn(level, parts):
-        api.sharded_step_dev(cache, low=lo.data_ptr(), up=hi.data_ptr(), rtol=rtol_T[0], atol=atol_T[0], level=level, nranks=parts.shape[0],
-                             partials=parts.data_ptr(), state=state.data_ptr(), stream=stream)
-
-    if shard_from_level is None:
-        shard_from_level = (max_levels + 1 if exchange == "peer" else 0) if world == 1 else (5 if dim == 3 else 8)
-    if exchange == "peer":
-        import ctypes as C
-        mb = PeerMailboxes.get(group)
-        mb.epoch += 1
-        L.check(L.lib.fts_adaptive_sharded_fused_dev(
-            cache.handle, f._h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(p.data_ptr()) if p is not None else None,
-            api._ptr(rtol_T), api._ptr(atol_T), max_levels, shard_from_level, rank, world, mb.ptrs, C.c_uint64(mb.epoch),
-            C.c_void_p(state.data_ptr()), C.c_void_p(stream)))
-    else:
-        run_sharded_levels(max_levels, rank, world, level_fn, step_fn, all_gather, shard_from_level)
-    s = state.cpu().numpy()  # the only host synchronisation
-    if s[5] == 3:
-        raise api.FtsError(L.ERR_CUDA, "sharded integral: a rank did not deliver its level partial within 2 s (peer exchange timed out)")
+    plan = ShardedPlan(T, f, low, up, rtol=rtol, atol=atol, max_levels=max_levels, cache=cache, params=params, group=group,
+                       shard_from_level=shard_from_level, exchange=exchange)
+    plan.launch()
+    s = plan.result()
+    dt, dim, rank = plan.dt, plan.dim, plan.rank
     conv = s[5] != 0
     flags = np.array([L.FLAG_CONVERGED if conv else (L.FLAG_MAX_LEVELS if max_levels > 0 else 0)], np.int32)
     res = api.AdaptiveResult(np.array([s[3]], dt), np.array([s[4]], dt), np.array([int(s[6])], np.int32), flags)

@@ -298,7 +298,7 @@ int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up,
  * the integral.  The epilogue of each level kernel stores this rank's (s, c) and then an epoch
  * flag straight into every rank's MAILBOX over NVLink peer memory (cudaIpc-mapped device
  * buffers), and the device-side stop test of every rank waits for the flags in its own mailbox
- * (2 s timeout -> state done = 3).  No NCCL call and no host involvement between levels; levels
+ * (timeout FTS_B200_PEER_TIMEOUT_MS, default 10 s -> state done = 3).  No NCCL call and no host involvement between levels; levels
  * below `shard_from_level` are too small to shard and are computed whole on every rank.
  * mailboxes[r] = rank r's mailbox mapped into this process (fts_peer_alloc on the owner,
  * fts_peer_open elsewhere; size fts_peer_mailbox_bytes); epoch = 1, 2, 3 ... incremented by the
@@ -313,6 +313,12 @@ int fts_adaptive_sharded_fused_dev(fts_cache c, fts_integrand f, const void* low
                                    int max_levels, int shard_from_level, int rank, int nranks,
                                    void* const* mailboxes, uint64_t epoch, void* state_dev,
                                    void* stream);
+
+/* Per-level exchange wait of the LAST fts_adaptive_sharded_fused_dev call of this process: out[l] =
+ * nanoseconds (%globaltimer) the device-side stop test of level l spent spinning on the slowest
+ * peer's flag (0 for levels computed whole on every rank).  Synchronises the device.  The spin
+ * gives up after FTS_B200_PEER_TIMEOUT_MS (environment, default 10000). */
+int fts_peer_wait_ns(int nlevels, uint64_t* out);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Register-resident DFMA (dtype FTS_F64) / FFMA (FTS_F32) chain microbenchmark: the measured

@@ -317,3 +317,61 @@ double fts_or_adaptive3d_level_sum_omp_f64(int fam, const double* p, const doubl
     for (int r = 0; r < nt * 8; ++r) total += fts_or_adaptive3d_level_sum_f64(&f, &bx, xl, wl, n, r, nt * 8);
     return total;
 }
+
+/* adaptive_integrate_3D (adaptive.jl:352-471) with every level's new-point sum split over OpenMP
+ * threads along the outer index i and accumulated in __float128: the exactly-summed value of the
+ * same T-rounded terms as fts_or_adaptive3d_f64x (the order of an exact sum does not matter to
+ * ~1e-34), but a level-8 integral (1.08e9 evaluations) takes seconds instead of a minute.  Used by
+ * the GPU parity tests at BASELINE config D depths (forced depth L = 7, 8). */
+void fts_or_adaptive3d_omp_f64x(int fam, const double* p, const double* low, const double* up,
+                                double rtol, double atol, int max_levels, double tm, const double* ix,
+                                const double* iw, const double* xs, const double* ws, int nthreads,
+                                fts_or_result_f64x* out)
+{
+    fts_or_fn_f64 f = {fam, p, NULL};
+    box3_f64x bx;
+    bx.dx = 0.5 * (up[0] - low[0]); bx.x0 = 0.5 * (up[0] + low[0]);
+    bx.dy = 0.5 * (up[1] - low[1]); bx.y0 = 0.5 * (up[1] + low[1]);
+    bx.dz = 0.5 * (up[2] - low[2]); bx.z0 = 0.5 * (up[2] + low[2]);
+    bx.w0 = half_pi_f64();
+    bx.w02 = bx.w0 * bx.w0;
+    int nt = nthreads > 0 ? nthreads : fts_or_num_threads();
+    double h = tm * 0.5;
+    __float128 s_total = fts_or_adaptive3d_level0_f64x(&f, &bx, ix, iw);
+    long evals = 125;
+#define SCALE3X(s) ((double)(((__float128)bx.dx * (__float128)bx.dy * (__float128)bx.dz * ((__float128)h * (__float128)h * (__float128)h)) * (s)))
+    double old_res = SCALE3X(s_total);
+    double err = 0;
+    out->level = 0;
+    out->converged = 0;
+    for (int level = 1; level <= max_levels; ++level) {
+        h *= 0.5;
+        long n = 2L << level, off = n - 4;
+        int parts = nt * 8;
+        if (parts > n) parts = (int)n;
+        __float128 partial[parts];
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 1)
+#endif
+        for (int r = 0; r < parts; ++r) partial[r] = fts_or_adaptive3d_level_sum_f64x(&f, &bx, xs + off, ws + off, n, r, parts);
+        __float128 s_new = 0;
+        for (int r = 0; r < parts; ++r) s_new += partial[r];
+        evals += 7 * n * n * n + 9 * n * n + 3 * n;
+        s_total += s_new;
+        double new_res = SCALE3X(s_total);
+        err = fabs(new_res - old_res);
+        out->level = level;
+        if (err <= err_target_f64x(new_res, rtol, atol)) {
+            out->value = new_res;
+            out->err = err;
+            out->converged = 1;
+            out->evals = evals;
+            return;
+        }
+        old_res = new_res;
+    }
+#undef SCALE3X
+    out->value = old_res;
+    out->err = err;
+    out->evals = evals;
+}

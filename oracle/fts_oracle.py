@@ -31,9 +31,27 @@ FAMILIES = {
 }
 
 
+def native_tag() -> str:
+    """Tag of this host's CPU (hash of its model name and ISA flags): -march=native builds are named
+    after it, so a library built on another machine (the built files travel with the repository
+    snapshot) is never loaded here."""
+    import hashlib
+    ident = ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith(("model name", "flags")):
+                    ident += line
+                if line.strip() == "" and ident:
+                    break
+    except OSError:
+        ident = "unknown"
+    return hashlib.sha1(ident.encode()).hexdigest()[:10]
+
+
 def build(native: bool = False) -> None:
     """Compile the oracle with the committed Makefile (gcc, a few seconds)."""
-    target = ["native"] if native else []
+    target = ["native", f"NATIVE_TAG={native_tag()}"] if native else []
     subprocess.run(["make", "-C", _HERE, "-s"] + target, check=True)
 
 
@@ -73,7 +91,7 @@ class Oracle:
 
     def __init__(self, variant: str = "strict"):
         name = {"strict": "libfts_oracle.so", "fast": "libfts_oracle_fast.so",
-                "native": "libfts_oracle_native.so"}[variant]
+                "native": f"libfts_oracle_native_{native_tag()}.so"}[variant]
         path = os.path.join(_BUILD, name)
         if not os.path.exists(path):
             build(native=(variant == "native"))
@@ -112,6 +130,9 @@ class Oracle:
             f.restype = None
             f.argtypes = [C.c_int, vp, vp, vp, ct, ct, C.c_int, ct, vp, vp, vp, vp, vp, vp, vp]
         L.fts_or_num_threads.restype = C.c_int
+        L.fts_or_adaptive3d_omp_f64x.restype = None
+        L.fts_or_adaptive3d_omp_f64x.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fts_or_adaptive3d_level_sum_omp_f64.restype = C.c_double
         L.fts_or_adaptive3d_level_sum_omp_f64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                           C.c_void_p, C.c_void_p, C.c_long, C.c_int]
@@ -251,6 +272,15 @@ class Oracle:
             _ptr(cache["ix"]), _ptr(cache["iw"]), _ptr(cache["xs"]), _ptr(cache["ws"]), C.byref(r))
         return self._out(r)
 
+    def adaptive3d_omp_f64x(self, fam, p, low, up, rtol, atol, max_levels, cache, nthreads: int = 0) -> Result:
+        """adaptive_integrate_3D (src/adaptive.jl:352-471), exactly summed (__float128), every level
+        split over OpenMP threads along the outer index: config D depths (L = 7, 8) in seconds."""
+        pa = self._p("f64", p); r = _Res64()
+        lo = np.ascontiguousarray(low, np.float64); hi = np.ascontiguousarray(up, np.float64)
+        self.lib.fts_or_adaptive3d_omp_f64x(fam, _ptr(pa), _ptr(lo), _ptr(hi), rtol, atol, max_levels, float(cache["tm"][0]),
+                                            _ptr(cache["ix"]), _ptr(cache["iw"]), _ptr(cache["xs"]), _ptr(cache["ws"]), nthreads, C.byref(r))
+        return self._out(r)
+
     def adaptive2d_cmpl(self, dtype, fam, p, low, up, rtol, atol, max_levels, cache) -> Result:
         nt = _np_t(dtype); ct = _c_t(dtype); pa = self._p(dtype, p); r = self._res(dtype)
         lo = np.ascontiguousarray(low, nt); hi = np.ascontiguousarray(up, nt)
@@ -339,6 +369,58 @@ class Oracle:
             _ptr(cache["xs"]), _ptr(cache["ws"]), _ptr(cache["cs"]), C.c_long(batch), _ptr(value), _ptr(err),
             _ptr(level), _ptr(conv), _ptr(evals), nthreads)
         return dict(value=value, err=err, level=level, converged=conv.astype(bool), evals=evals)
+
+
+# ---------------------------------------------------------------------- `@turbo` twins ---------
+class OracleAvx:
+    """CPU twin of the reference's LoopVectorization kernels (oracle/fts_oracle_avx.c: SIMD
+    reductions + vector libm, -O3 -march=native -ffast-math): the timed CPU baseline of bench.py."""
+
+    def __init__(self, wide: bool = False):
+        """wide=True: the build with 512-bit vectors forced (-mprefer-vector-width=512)"""
+        path = os.path.join(_BUILD, f"libfts_oracle_avx{'512' if wide else ''}_{native_tag()}.so")
+        if not os.path.exists(path):
+            build(native=True)
+        self.lib = C.CDLL(path)
+        vp = C.c_void_p
+        self.lib.fts_or_avx_batch_adaptive1d_f64.restype = C.c_int
+        self.lib.fts_or_avx_batch_adaptive1d_f64.argtypes = [C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                                             vp, vp, vp, vp, C.c_long, vp, vp, vp, C.c_int]
+        self.lib.fts_or_avx_batch_integrate1d_f64.restype = C.c_int
+        self.lib.fts_or_avx_batch_integrate1d_f64.argtypes = [C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_double, C.c_long, vp, C.c_int]
+
+    def num_threads(self) -> int:
+        return self.lib.fts_or_avx_num_threads()
+
+    def vector_bits(self) -> int:
+        """widest vector ISA the build may use (gcc still prefers 256-bit unless wide=True)"""
+        return self.lib.fts_or_avx_vector_bits()
+
+    def batch_adaptive1d(self, fam, params, low, up, rtol, atol, max_levels, cache, nthreads: int = 0):
+        """adaptive_integrate_1D_avx (src/adaptive.jl:94-133) looped over a batch (README.md:96-106)"""
+        params = np.ascontiguousarray(params, np.float64).reshape(-1)
+        low = np.ascontiguousarray(low, np.float64).reshape(-1); up = np.ascontiguousarray(up, np.float64).reshape(-1)
+        batch = max(params.size, low.size)
+        value = np.zeros(batch); level = np.zeros(batch, np.int32); evals = np.zeros(batch, np.int64)
+        rc = self.lib.fts_or_avx_batch_adaptive1d_f64(fam, _ptr(params), 1 if params.size > 1 else 0, _ptr(low), _ptr(up), 1 if low.size > 1 else 0,
+                                                      rtol, atol, max_levels, float(cache["tm"][0]), _ptr(cache["ix"]), _ptr(cache["iw"]),
+                                                      _ptr(cache["xs"]), _ptr(cache["ws"]), batch, _ptr(value), _ptr(level), _ptr(evals), nthreads)
+        if rc:
+            raise ValueError("the @turbo twin covers the headline families only (F1_GAUSS, F1_EXP)")
+        return dict(value=value, level=level, evals=evals)
+
+    def batch_integrate1d(self, fam, params, low, up, x, w, h, nthreads: int = 0):
+        """integrate1D_avx (src/integrate1D.jl:138-147) over a batch"""
+        low = np.ascontiguousarray(low, np.float64).reshape(-1); up = np.ascontiguousarray(up, np.float64).reshape(-1)
+        params = None if params is None else np.ascontiguousarray(params, np.float64).reshape(-1)
+        batch = max(low.size, params.size if params is not None else 1)
+        value = np.zeros(batch)
+        x = np.ascontiguousarray(x, np.float64); w = np.ascontiguousarray(w, np.float64)
+        rc = self.lib.fts_or_avx_batch_integrate1d_f64(fam, _ptr(params) if params is not None else None, 1 if (params is not None and params.size > 1) else 0,
+                                                       _ptr(low), _ptr(up), 1 if low.size > 1 else 0, _ptr(x), _ptr(w), x.size, float(h), batch, _ptr(value), nthreads)
+        if rc:
+            raise ValueError("the @turbo twin covers the headline families only (F1_GAUSS, F1_EXP)")
+        return value
 
 
 # ---------------------------------------------------------------------- optimal-spacing grids --

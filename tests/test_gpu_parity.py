@@ -50,16 +50,16 @@ def rel(a, b):
 
 
 # ------------------------------------------------------------------ reference golden vectors --
-def _gold_rows(kinds):
+def _gold_rows(kinds, max_dim=3):
     seen = set()
     for r in GOLD["rows"]:
         key = (r["function"], r["kind"], r["value"])
-        if r["kind"] in kinds and key not in seen and r["dim"] < 3:
+        if r["kind"] in kinds and key not in seen and r["dim"] <= max_dim:
             seen.add(key)
             yield r
 
 
-@pytest.mark.parametrize("row", list(_gold_rows({"adaptive"})), ids=lambda r: f"{r['function']}-{r['source'].split('/')[-1]}")
+@pytest.mark.parametrize("row", list(_gold_rows({"adaptive"}, max_dim=2)), ids=lambda r: f"{r['function']}-{r['source'].split('/')[-1]}")
 def test_reference_csv_adaptive_rows(gpu, row):
     """adaptive_integrate_{1,2}D at the reference's benchmark settings reproduce the values the
     reference printed, at the reference's stop level (3D rows: test_reference_csv_3d_rows)."""
@@ -95,14 +95,15 @@ def test_reference_csv_3d_rows(gpu, oracle):
 
 @pytest.mark.parametrize("row", list(_gold_rows({"avx"})), ids=lambda r: f"{r['function']}-{r['source'].split('/')[-1]}")
 def test_reference_csv_fixed_grid_rows(gpu, row):
-    """integrate{1,2}D_avx rows: both summation orders land within the documented distance of the
+    """integrate{1,2,3}D_avx rows (3D: timings_julia1.12.csv:75,84,93 — N = 32 / 64 / 64, up to
+    274 625 evaluations): both summation orders land within the documented distance of the
     reference's @turbo value (problems.CSV_RTOL explains the endpoint-singular rows)."""
     dim, fam, p, low, up = CSV_PROBLEMS[row["function"]]
     x, w, h = gpu.tanhsinh(np.float64, row["N"])
     gold = float(row["value"])
     tol = CSV_RTOL.get((row["function"], "avx"), 4e-15)
     f = gpu.builtin(NAME_OF[fam])
-    fn = gpu.integrate1D if dim == 1 else gpu.integrate2D
+    fn = {1: gpu.integrate1D, 2: gpu.integrate2D, 3: gpu.integrate3D}[dim]
     for order in ("reference", "fast"):
         v = fn(f, low, up, x, w, h, params=p, order=order)
         assert rel(v, gold) <= tol, (order, v, gold)
@@ -114,26 +115,36 @@ def _alpha(n):
 
 
 def test_config_b_against_oracle(gpu, oracle):
-    """BASELINE configs[1] at 8192 integrals: (value, level) against the oracle; integrals whose
-    error estimate sits within 1e-5 of the stop threshold may stop one level apart
-    and are counted separately."""
-    n = 8192
+    """BASELINE configs[1] at its OWN size: all 2^20 (value, level) pairs against the oracle (OpenMP
+    over the batch).  Equal stop level -> value <= 1e-14 relative; integrals whose error estimate sits
+    within 1e-5 of the stop threshold may stop one level apart: every one of them is
+    counted and proven borderline with a forced-depth oracle call."""
+    n = 1 << 20
     a = _alpha(n)
     cache = gpu.adaptive_cache_1D(np.float64, max_levels=16)
     r = gpu.quad(gpu.builtin("gauss"), -1.0, 1.0, rtol=1e-10, max_levels=16, cache=cache, params=a, order="reference", full_output=True)
-    ref = oracle.batch_adaptive1d("f64", F["F1_GAUSS"], a, [-1.0], [1.0], 1e-10, 0.0, 16, oracle.cache1d("f64", 16))
+    oc = oracle.cache1d("f64", 16)
+    ref = oracle.batch_adaptive1d("f64", F["F1_GAUSS"], a, [-1.0], [1.0], 1e-10, 0.0, 16, oc)
     same = r.levels == ref["level"]
     assert rel(r.value[same], ref["value"][same]).max() <= RTOL64
     assert rel(r.err[same], ref["err"][same]).max() <= 1e-3 or np.abs(r.err[same] - ref["err"][same]).max() <= 1e-15
     flipped = np.nonzero(~same)[0]
-    assert flipped.size <= n // 1000, f"{flipped.size} stop-level flips"
+    assert flipped.size <= n // 10000, f"{flipped.size} stop-level flips"
     for i in flipped:  # borderline: err_est / target within 1e-5 of 1 at the earlier level
+        assert abs(int(r.levels[i]) - int(ref["level"][i])) == 1
         lvl = min(r.levels[i], ref["level"][i])
-        rr = oracle.adaptive1d("f64", F["F1_GAUSS"], [a[i]], -1.0, 1.0, 0.0, 0.0, int(lvl), oracle.cache1d("f64", 16))
+        rr = oracle.adaptive1d("f64", F["F1_GAUSS"], [a[i]], -1.0, 1.0, 0.0, 0.0, int(lvl), oc)
         assert abs(rr.err / (1e-10 * abs(rr.value)) - 1) < 1e-5
-    assert r.converged.all() and set(np.unique(r.levels)) <= {4, 5, 6}
-    exact = np.sqrt(PI / a) * np.array([math.erf(math.sqrt(v)) for v in a])
-    assert rel(r.value, exact).max() < 1e-10
+        assert rel(r.value[i], ref["value"][i]) <= 2e-10      # both estimates meet the requested tolerance
+    assert r.converged.all() and np.array_equal(r.converged, ref["converged"]) and set(np.unique(r.levels)) <= {4, 5, 6}
+    assert np.array_equal(gpu.evals_for_level(1, r.levels)[same], ref["evals"][same])
+    from scipy.special import erf
+    assert rel(r.value, np.sqrt(PI / a) * erf(np.sqrt(a))).max() < 1e-10
+    # the same set shuffled (seed 0, what bench.py --permute runs): the device-side level bucketing
+    # must not change a single bit
+    perm = np.random.default_rng(0).permutation(n)
+    rp = gpu.quad(gpu.builtin("gauss"), -1.0, 1.0, rtol=1e-10, max_levels=16, cache=cache, params=a[perm], order="reference", full_output=True)
+    assert np.array_equal(rp.value, r.value[perm]) and np.array_equal(rp.levels, r.levels[perm]) and np.array_equal(rp.err, r.err[perm])
 
 
 def test_config_b_full_size_properties(gpu):
@@ -761,6 +772,84 @@ def test_on_device_table_generation(gpu):
     vd = gpu.quad_cmpl(gpu.builtin("c_exp_inv_bmx"), gpu.to_dd([0.0]), gpu.to_dd([1.0]), rtol="1e-28", max_levels=12,
                        cache=gpu.adaptive_cache_1D(gpu.Double64, max_levels=12, complement=True, on_device=True))
     assert abs(gpu.dd_to_mpf(vd)[0] - (mpmath.exp(-1) - mpmath.e1(1))) < mpmath.mpf("1e-28")
+
+
+# ------------------------------------------------------------------ BASELINE sizes: D and E ---
+@pytest.mark.parametrize("box", ["unit", "aniso"])
+def test_config_d_deep_levels_against_oracle(gpu, oracle, box):
+    """BASELINE configs[3] at its quoted depths: adaptive_integrate_3D_avx of exp(x+y+z) at forced
+    depth L = 7 and 8 (135 M / 1.08 G evaluations; rtol = atol = 0, the reference's own regression
+    mode, runtests.jl:230) on [-1,1]^3 and on [-2,3]x[-1,2]x[0,4] (test/families_3d.jl:26-27),
+    against the oracle's exactly-summed value of the same terms (OpenMP over the outer index)."""
+    lo, up = ([-1.0] * 3, [1.0] * 3) if box == "unit" else ([-2.0, -1.0, 0.0], [3.0, 2.0, 4.0])
+    exact = np.prod(np.exp(up) - np.exp(lo))
+    oc = oracle.cache_tensor("f64", 3, 8)
+    cache = gpu.adaptive_cache_3D(np.float64, max_levels=8)
+    f = gpu.builtin("exp_3d")
+    for L in (7, 8):
+        refx = oracle.adaptive3d_omp_f64x(F["F3_EXP"], None, lo, up, 0.0, 0.0, L, oc)
+        assert refx.level == L and refx.evals == (2 * (2 << L) + 1) ** 3
+        r = gpu.adaptive_integrate_3D_avx(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, warn=False, cache=cache, full_output=True)
+        assert r.levels[0] == L and int(gpu.evals_for_level(3, r.levels)[0]) == refx.evals
+        assert rel(r.value[0], refx.value) <= RTOL64, (box, L, r.value[0], refx.value)
+        assert rel(r.err[0], refx.err) <= 1e-3 or abs(r.err[0] - refx.err) <= 1e-14 * abs(refx.value)
+        assert rel(r.value[0], exact) <= 1e-12
+        # the multi-GPU entry point on one rank (fused exchange path and the all-gather path) gives the same integral
+        from fts_b200 import distributed as fd
+        for exchange in ("peer", "nccl"):
+            rs = fd.adaptive_integrate_sharded(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, cache=cache, exchange=exchange, warn=False)
+            assert rs.levels[0] == L and rel(rs.value[0], refx.value) <= RTOL64, (box, L, exchange)
+    # tolerance mode (SURVEY 8d: rtol = 1e-9): same stop level as the oracle
+    refx = oracle.adaptive3d_omp_f64x(F["F3_EXP"], None, lo, up, 1e-9, 0.0, 8, oc)
+    r = gpu.adaptive_integrate_3D_avx(np.float64, f, lo, up, rtol=1e-9, max_levels=8, cache=cache, full_output=True)
+    assert r.converged[0] and r.levels[0] == refx.level and rel(r.value[0], refx.value) <= RTOL64
+
+
+def test_config_e_full_size(gpu, oracle):
+    """BASELINE configs[4] at its own size: 65 536 Double64 quad_cmpl integrals, rtol 1e-28.
+    Every value against the closed form in 50-digit arithmetic (c*pi and (b-a)(ln(b-a)-1)), one in
+    256 against the __float128 oracle (parity unpinned by the reference), plus
+    permutation invariance (bit-identical hi and lo words)."""
+    import mpmath
+    mpmath.mp.dps = 50
+    rng = np.random.default_rng(0)
+    n = 65536
+    a = -3 * rng.random(n); b = 0.5 + 3.5 * rng.random(n); c = 0.5 + 1.5 * rng.random(n)   # SURVEY 8d input E
+    cache = gpu.adaptive_cache_1D(gpu.Double64, max_levels=16, complement=True)
+    oc = oracle.cache1d("dd", 16, True)
+    z = np.zeros(n)
+    pick = np.arange(0, n, 256)
+    tol = mpmath.mpf("1e-28")
+    for name, fam in (("c_invsqrt", F["C1_INVSQRT"]), ("c_log_bmx", F["C1_LOG_BMX"])):
+        par = gpu.to_dd(c) if name == "c_invsqrt" else None
+        r = gpu.quad_cmpl(gpu.builtin(name), gpu.to_dd(a), gpu.to_dd(b), rtol="1e-28", max_levels=16, cache=cache, params=par, full_output=True)
+        assert r.converged.all()
+        got = gpu.dd_to_mpf(r.value)
+        worst = mpmath.mpf(0)
+        for i in range(n):
+            if name == "c_invsqrt":
+                want = mpmath.mpf(float(c[i])) * mpmath.pi
+            else:
+                w_ = mpmath.mpf(float(b[i])) - mpmath.mpf(float(a[i]))
+                want = w_ * (mpmath.log(w_) - 1)
+            worst = max(worst, abs(got[i] - want) / abs(want))
+        # the stop rule guarantees |I_L - I_(L-1)| <= 1e-28 |I|; the distance to the exact value is smaller still
+        assert worst <= mpmath.mpf("1e-27"), (name, worst)
+        ref = oracle.batch_adaptive1d_cmpl_dd(fam, oracle.dd_join(c[pick], z[pick]), 1, oracle.dd_join(a[pick], z[pick]), oracle.dd_join(b[pick], z[pick]), 1,
+                                              oracle.q_from_str("1e-28"), oracle.q_from_str("0"), 16, oc)
+        nsame = 0
+        for k, i in enumerate(pick):
+            want = mpmath.mpf(oracle.q_to_str(ref["value"][k:k + 1]))
+            if r.levels[i] == ref["level"][k]:
+                nsame += 1
+                assert abs(got[i] - want) <= tol * abs(want), (name, i)
+            else:
+                assert abs(int(r.levels[i]) - int(ref["level"][k])) == 1 and abs(got[i] - want) <= 10 * tol * abs(want), (name, i)
+        assert nsame >= 0.9 * pick.size, (name, nsame)
+        perm = np.random.default_rng(1).permutation(n)
+        rp = gpu.quad_cmpl(gpu.builtin(name), gpu.to_dd(a[perm]), gpu.to_dd(b[perm]), rtol="1e-28", max_levels=16, cache=cache,
+                           params=gpu.to_dd(c[perm]) if par is not None else None, full_output=True)
+        assert np.array_equal(rp.value, r.value[perm]) and np.array_equal(rp.levels, r.levels[perm])
 
 
 # ------------------------------------------------------------------ family sweep --------------

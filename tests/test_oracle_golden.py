@@ -262,3 +262,37 @@ def test_double64_standin(oracle):
     mpmath.mp.dps = 40
     assert abs(mpmath.mpf(s) - mpmath.pi) < mpmath.mpf("1e-28") * mpmath.pi
     assert out["converged"][0]
+
+
+def test_openmp_exact_3d_equals_sequential_exact_3d(oracle):
+    """fts_or_adaptive3d_omp_f64x (the checker of the config-D depths on the GPU) is the same exact
+    sum as the sequential f64x kernel: identical doubles, levels and evaluation counts."""
+    c3 = oracle.cache_tensor("f64", 3, 5)
+    for lo, up in (([-1.0] * 3, [1.0] * 3), ([-2.0, -1.0, 0.0], [3.0, 2.0, 4.0])):
+        for rtol, L in ((0.0, 4), (1e-9, 5)):
+            seq = oracle.adaptive_nd("f64x", 3, F["F3_EXP"], None, lo, up, rtol, 0.0, L, c3)
+            for nt in (1, 3, 0):
+                par = oracle.adaptive3d_omp_f64x(F["F3_EXP"], None, lo, up, rtol, 0.0, L, c3, nthreads=nt)
+                assert (par.value, par.err, par.level, par.converged, par.evals) == (seq.value, seq.err, seq.level, seq.converged, seq.evals)
+
+
+def test_turbo_twin_against_scalar_oracle(oracle):
+    """The `@turbo` twins (oracle/fts_oracle_avx.c: adaptive_integrate_1D_avx adaptive.jl:94-133,
+    integrate1D_avx integrate1D.jl:138-147 — SIMD reductions, vector libm, FMA) agree with the
+    scalar kernels to the reference's own avx-vs-scalar tolerances (runtests.jl:155-160: 1e-12..1e-14)."""
+    from fts_oracle import OracleAvx
+    a = 0.5 + 49.5 * np.arange(4096) / 4095
+    c = oracle.cache1d("f64", 16)
+    ref = oracle.batch_adaptive1d("f64", F["F1_GAUSS"], a, [-1.0], [1.0], 1e-10, 0.0, 16, c)
+    for wide in (False, True):
+        tw = OracleAvx(wide)
+        got = tw.batch_adaptive1d(F["F1_GAUSS"], a, [-1.0], [1.0], 1e-10, 0.0, 16, c)
+        same = got["level"] == ref["level"]
+        assert same.mean() > 0.995
+        assert np.max(np.abs(got["value"][same] - ref["value"][same]) / ref["value"][same]) < 1e-14
+        assert np.array_equal(got["evals"][same], ref["evals"][same])
+        x, w, h = oracle.tanhsinh("f64", 256)
+        ups = 1.0 + np.arange(33) / 32.0
+        v = tw.batch_integrate1d(F["F1_EXP"], None, np.zeros(33), ups, x, w, h)
+        vs = np.array([oracle.integrate1d("f64", F["F1_EXP"], None, 0.0, u, x, w, h) for u in ups])
+        assert np.max(np.abs(v - vs) / vs) < 1e-14 and np.max(np.abs(v - (np.exp(ups) - 1))) < 1e-13
