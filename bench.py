@@ -267,7 +267,8 @@ def host_link_ceiling(dev, world, dist, in_bytes: int, out_bytes: int, reps: int
 def sharded3d_record(fts, dev, world, rank, dist, levels, reps: int):
     """BASELINE configs[3] ("integrate3D adaptive with adaptive_cache_3D, single large integral sharded
     over outer axis"): adaptive_integrate_3D_avx (adaptive.jl:489-706) of exp(x+y+z) and
-    log(1-x)log(1-y)log(1-z) on [-1,1]^3 at forced depth L through the fused peer-memory exchange
+    log(1-x)log(1-y)log(1-z) on [-1,1]^3 at forced depth L (FTS_OPT_FORCE_DEPTH: with rtol = atol = 0 alone
+    exp(x+y+z) stops at level 6, where two levels agree to the last bit) through the fused peer-memory exchange
     and the NCCL all-gather variant.  Strong scaling: the N = 1 arm is every rank computing the whole
     integral on its own GPU (no exchange); times are CUDA events, max over ranks, median over reps."""
     import torch
@@ -284,7 +285,7 @@ def sharded3d_record(fts, dev, world, rank, dist, levels, reps: int):
             if world > 1:
                 arms += [("fused_peer", dict(exchange="peer")), ("nccl_allgather", dict(exchange="nccl"))]
             for arm, kw in arms:
-                plan = fd.ShardedPlan(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, cache=cache, **kw)
+                plan = fd.ShardedPlan(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, cache=cache, force_depth=True, **kw)
                 ts = []
                 for it in range(reps + 2):
                     if world > 1:

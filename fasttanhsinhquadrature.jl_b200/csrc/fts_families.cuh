@@ -54,6 +54,7 @@ struct F1Poly7 {
 struct F1Exp {
     static constexpr int NP = 0;
     static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_EXP_TAB = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::exp(x); }
     template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N]) { exp_n<N, MODE>(x, f); }
     template <class T> static __device__ __forceinline__ T exp_arg_bound(T reach, const T*) { return reach; }  // max |x| over the interval
@@ -61,6 +62,7 @@ struct F1Exp {
 struct F1Gauss {  // exp(-α*x^2)   README.md:102
     static constexpr int NP = 1;
     static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_EXP_TAB = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p) { return fm::exp(-p[0] * (x * x)); }
     template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T* p, T (&f)[N])
     {
@@ -78,19 +80,47 @@ struct F1Runge {  // 1/(1+25x^2)   benchmarks.jl:34
         return num<T>::one() / muladd<T, FAST>(p[0], x * x, num<T>::one());
     }
 };
+// log families: fm::log_tab is the table-driven log of fts_math.cuh (Float64; <= 0.72 ulp), evaluated in
+// lock-step for the N points a kernel hands over at once
 struct F1Log1mx {
     static constexpr int NP = 0;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::log(num<T>::one() - x); }
+    static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_LOG_TAB = true;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::log_tab(num<T>::one() - x); }
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = num<T>::one() - x[i];
+        log_n<N>(a, f);
+    }
 };
 struct F1Log1px {
     static constexpr int NP = 0;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::log(num<T>::one() + x); }
+    static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_LOG_TAB = true;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*) { return fm::log_tab(num<T>::one() + x); }
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = num<T>::one() + x[i];
+        log_n<N>(a, f);
+    }
 };
 struct F1InvSqrt1mx2 {  // 1/sqrt(1-x^2)   benchmarks.jl:36
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T*)
     {
         return fm::inv_sqrt<FAST>(muladd<T, FAST>(-x, x, num<T>::one()));
+    }
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = muladd<T, FAST>(-x[i], x[i], num<T>::one());
+        inv_sqrt_n<FAST>(a, f);
     }
 };
 struct F1Sin2 {  // sin(1000x)^2   benchmarks.jl:37
@@ -122,11 +152,13 @@ struct C1InvSqrt {  // c/sqrt(bmx*xma)   test/runtests.jl:82, families_1d.jl:10
 };
 struct C1LogBmx {
     static constexpr int NP = 0;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T, const T*) { return fm::log(bmx); }
+    static constexpr bool USES_LOG_TAB = true;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T, const T*) { return fm::log_tab(bmx); }
 };
 struct C1LogXma {
     static constexpr int NP = 0;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T xma, const T*) { return fm::log(xma); }
+    static constexpr bool USES_LOG_TAB = true;
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T xma, const T*) { return fm::log_tab(xma); }
 };
 struct C1ExpInvBmx {  // exp(-1/bmx)   families_1d.jl:41
     static constexpr int NP = 0;
@@ -148,6 +180,7 @@ struct F2Poly2 {
 struct F2Exp {
     static constexpr int NP = 0;
     static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_EXP_TAB = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return fm::exp(x + y); }
     template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T*, T (&f)[N])
     {
@@ -164,30 +197,65 @@ struct F2X2pY2 {
 };
 struct F2InvSqrt {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*)
     {
         const T one = num<T>::one();
         return fm::inv_sqrt<FAST>(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one));
     }
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T*, T (&f)[N])
+    {
+        const T one = num<T>::one();
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = muladd<T, FAST>(-x[i], x[i], one) * muladd<T, FAST>(-y[i], y[i], one);
+        inv_sqrt_n<FAST>(a, f);
+    }
 };
 struct F2InvSqrtAbs {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, const T*) { return fm::inv_sqrt<FAST>(fm::abs(x * y)); }
+    template <class T, bool FAST, int N, int MODE> static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = fm::abs(x[i] * y[i]);
+        inv_sqrt_n<FAST>(a, f);
+    }
 };
 
 // ---------------------------------------------------------------- 2D complement -------------
 struct C2InvSqrtBmxYmc {  // 1/sqrt((b-x)(y-c))   BASELINE config C
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T bmx, T, T, T ymc, const T*)
     {
         return fm::inv_sqrt<FAST>(bmx * ymc);
     }
+    template <class T, bool FAST, int N, int MODE>
+    static __device__ __forceinline__ void evaln(const T (&)[N], const T (&)[N], const T (&bmx)[N], const T (&)[N], const T (&)[N], const T (&ymc)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = bmx[i] * ymc[i];
+        inv_sqrt_n<FAST>(a, f);
+    }
 };
 struct C2InvSqrtAll {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T, T bmx, T xma, T dmy, T ymc, const T*)
     {
         return fm::inv_sqrt<FAST>(bmx * xma * dmy * ymc);
+    }
+    template <class T, bool FAST, int N, int MODE>
+    static __device__ __forceinline__ void evaln(const T (&)[N], const T (&)[N], const T (&bmx)[N], const T (&xma)[N], const T (&dmy)[N], const T (&ymc)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = bmx[i] * xma[i] * dmy[i] * ymc[i];
+        inv_sqrt_n<FAST>(a, f);
     }
 };
 
@@ -205,6 +273,7 @@ struct F3Poly2 {
 struct F3Exp {
     static constexpr int NP = 0;
     static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_EXP_TAB = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return fm::exp(x + y + z); }
     template <class T, bool FAST, int N, int MODE>
     static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T*, T (&f)[N])
@@ -222,10 +291,20 @@ struct F3X2Y2Z2 {
 };
 struct F3InvSqrt {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*)
     {
         const T one = num<T>::one();
         return fm::inv_sqrt<FAST>(muladd<T, FAST>(-x, x, one) * muladd<T, FAST>(-y, y, one) * muladd<T, FAST>(-z, z, one));
+    }
+    template <class T, bool FAST, int N, int MODE>
+    static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T*, T (&f)[N])
+    {
+        const T one = num<T>::one();
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = muladd<T, FAST>(-x[i], x[i], one) * muladd<T, FAST>(-y[i], y[i], one) * muladd<T, FAST>(-z[i], z[i], one);
+        inv_sqrt_n<FAST>(a, f);
     }
 };
 struct F3Rat {
@@ -237,17 +316,72 @@ struct F3Rat {
                       muladd<T, FAST>(num<T>::from_double(9.0), z * z, one));
     }
 };
-struct F3Log {
+struct F3Log {  // log(1-x) log(1-y) log(1-z)   benchmarks.jl:45
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
+    static constexpr bool USES_LOG_TAB = true;
+    static constexpr bool HAS_CELLS_RUN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*)
     {
         const T one = num<T>::one();
-        return fm::log(one - x) * fm::log(one - y) * fm::log(one - z);
+        return fm::log_tab(one - x) * fm::log_tab(one - y) * fm::log_tab(one - z);
+    }
+    // N points at once: 3N logs in lock-step (the compiler merges the duplicates — the 8 reflections of
+    // a cell have only 2 distinct x, y and z each)
+    template <class T, bool FAST, int N, int MODE>
+    static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T*, T (&f)[N])
+    {
+        const T one = num<T>::one();
+        T a[3 * N], l[3 * N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            a[i] = one - x[i];
+            a[N + i] = one - y[i];
+            a[2 * N + i] = one - z[i];
+        }
+        log_n<3 * N>(a, l);
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = l[i] * l[N + i] * l[2 * N + i];
+    }
+    // CH cells along k that share (x+-, y+-): sum_c w[c] * (sum of the 8 reflections of cell c), every value
+    // formed exactly as eval() forms it, (log(1-x) log(1-y)) log(1-z), and added in the order of cell3 — but the
+    // four x/y logs and their four products are computed once per run instead of once per reflection
+    // (what a compiler's common-subexpression elimination does to the reference's k-loop, adaptive.jl:600-607)
+    template <class T, int CH>
+    static __device__ __forceinline__ T cells_run(T xp, T xm, T yp, T ym, const T (&zp)[CH], const T (&zm)[CH], const T (&w)[CH], const T*)
+    {
+        const T one = num<T>::one();
+        T a[4 + 2 * CH], l[4 + 2 * CH];
+        a[0] = one - xp; a[1] = one - xm; a[2] = one - yp; a[3] = one - ym;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            a[4 + c] = one - zp[c];
+            a[4 + CH + c] = one - zm[c];
+        }
+        log_n<4 + 2 * CH>(a, l);
+        const T pp = l[0] * l[2], mp = l[1] * l[2], pm = l[0] * l[3], mm = l[1] * l[3];  // (x+,y+) (x-,y+) (x+,y-) (x-,y-)
+        T acc = num<T>::zero();
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const T lzp = l[4 + c], lzm = l[4 + CH + c];
+            const T f = ((pp * lzp + mp * lzp) + (pm * lzp + mm * lzp)) + ((pp * lzm + mp * lzm) + (pm * lzm + mm * lzm));
+            acc = fm::fma(w[c], f, acc);
+        }
+        return acc;
     }
 };
 struct F3InvSqrtAbs {
     static constexpr int NP = 0;
+    static constexpr bool HAS_EVALN = true;
     template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, T y, T z, const T*) { return fm::inv_sqrt<FAST>(fm::abs(x * y * z)); }
+    template <class T, bool FAST, int N, int MODE>
+    static __device__ __forceinline__ void evaln(const T (&x)[N], const T (&y)[N], const T (&z)[N], const T*, T (&f)[N])
+    {
+        T a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = fm::abs(x[i] * y[i] * z[i]);
+        inv_sqrt_n<FAST>(a, f);
+    }
 };
 
 }  // namespace fts

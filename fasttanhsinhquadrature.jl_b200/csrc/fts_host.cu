@@ -31,13 +31,11 @@ long fts_tg_opt(int dtype, int N, double d, int D, long capacity, void* x, void*
 namespace {
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
-std::mutex g_mu;
+std::mutex g_mu;  // lifecycle and cold paths only; the launch entry points do not take it
 bool g_inited = false;
 int g_device = -1;
 cudaDeviceProp g_prop;
-cudaStream_t g_stream = nullptr;  // internal stream of the host-buffer entry points
-cudaStream_t g_pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of fts_adaptive_batch
-cudaEvent_t g_pipe_ev = nullptr;
+cudaStream_t g_stream = nullptr;  // stream of the cold paths (table generation, peak measurement), used under g_mu
 unsigned long long* g_peer_wait = nullptr;  // [64] device: per-level exchange wait of the last fused sharded call (ns)
 
 std::vector<KernelEntry>& registry()
@@ -106,7 +104,56 @@ struct Scratch {
     }
 };
 enum { S_LOW, S_UP, S_PAR, S_VAL, S_ERR, S_LVL, S_FLG, S_COUNT };
-Scratch g_scratch[S_COUNT];
+
+// Host-buffer entry points (fts_adaptive_batch, fts_integrate_batch, ...) are re-entrant: every HOST
+// THREAD owns a context — its own non-blocking stream, chunk-pipeline streams and grow-only device
+// scratch — so two threads drive two streams side by side without a lock (the reference's kernels
+// are lock-free too; only its cache memo takes a ReentrantLock, caches.jl:51).  Contexts are created
+// on a thread's first call and re-armed after fts_shutdown / re-binding (generation counter).
+struct HostCtx {
+    unsigned long long gen = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+    Scratch scratch[S_COUNT];
+};
+std::mutex g_ctx_mu;
+std::vector<HostCtx*> g_ctxs;  // never freed: a thread keeps its pointer; the CUDA resources inside are dropped at shutdown
+std::atomic<unsigned long long> g_gen{1};
+
+void drop_host_contexts()  // fts_shutdown / re-binding; must not race with running calls
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (HostCtx* c : g_ctxs) {
+        for (auto& sc : c->scratch) { if (sc.p) cudaFree(sc.p); sc.p = nullptr; sc.cap = 0; }
+        if (c->stream) cudaStreamDestroy(c->stream);
+        for (auto& ps : c->pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
+        if (c->ev) cudaEventDestroy(c->ev);
+        c->stream = nullptr; c->ev = nullptr; c->gen = 0;
+    }
+    g_gen.fetch_add(1);
+    cudaGetLastError();
+}
+
+int host_ctx(HostCtx** out)
+{
+    thread_local HostCtx* ctx = nullptr;
+    if (!ctx) {
+        ctx = new HostCtx();
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        g_ctxs.push_back(ctx);
+    }
+    if (ctx->gen != g_gen.load()) {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        FTS_CUDA(cudaSetDevice(g_device));  // the current device is a per-thread setting
+        FTS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto& ps : ctx->pipe) FTS_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+        FTS_CUDA(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+        ctx->gen = g_gen.load();
+    }
+    *out = ctx;
+    return FTS_OK;
+}
 }  // namespace
 
 namespace fts_host {
@@ -180,13 +227,10 @@ extern "C" int fts_init(int device)
     if (g_prop.major != 10)
         return set_error(FTS_ERR_NO_DEVICE, std::string("fts_b200 kernels are built for sm_100a only; device is ") + g_prop.name);
     if (g_inited && g_device != device) {
-        // re-binding: drop per-device scratch
-        for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+        // re-binding: drop everything that lives on the old device
+        drop_host_contexts();
         drop_device_state();
         if (g_stream) cudaStreamDestroy(g_stream);
-        for (auto& ps : g_pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
-        if (g_pipe_ev) cudaEventDestroy(g_pipe_ev);
-        g_pipe_ev = nullptr;
         g_stream = nullptr;
     }
     if (!g_stream) {
@@ -200,8 +244,6 @@ extern "C" int fts_init(int device)
         }
         cudaGetLastError();
         FTS_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-        for (auto& ps : g_pipe) FTS_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
-        FTS_CUDA(cudaEventCreateWithFlags(&g_pipe_ev, cudaEventDisableTiming));
     }
     g_device = device;
     g_inited = true;
@@ -212,12 +254,9 @@ extern "C" int fts_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return FTS_OK;
-    for (auto& s : g_scratch) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+    drop_host_contexts();
     drop_device_state();
     if (g_stream) cudaStreamDestroy(g_stream);
-    for (auto& ps : g_pipe) { if (ps) cudaStreamDestroy(ps); ps = nullptr; }
-    if (g_pipe_ev) cudaEventDestroy(g_pipe_ev);
-    g_pipe_ev = nullptr;
     g_stream = nullptr;
     g_inited = false;
     return FTS_OK;
@@ -657,20 +696,62 @@ static double elem_hi(int dtype, const void* p) { return dtype == FTS_F32 ? (dou
 // statically (reduction scratch, flags, the 4 KiB exp table region)
 static size_t dyn_smem_limit() { return (size_t)g_prop.sharedMemPerBlockOptin - 8192; }
 
+// opt-in dynamic shared memory above 48 KiB: set once per kernel and size (the attribute call costs a
+// microsecond or two, which a 30 us launch notices)
+static int ensure_dyn_smem(const void* fn, size_t smem)
+{
+    if (smem <= 40 * 1024) return FTS_OK;
+    if (smem > dyn_smem_limit())
+        return set_error(FTS_ERR_UNSUPPORTED, "level needs " + std::to_string(smem) + " B of shared memory per CTA (max " +
+                                                  std::to_string(dyn_smem_limit()) + ")");
+    thread_local std::vector<std::pair<const void*, size_t>> done;  // per host thread: no lock on the launch path
+    for (auto& e : done)
+        if (e.first == fn) {
+            if (e.second >= smem) return FTS_OK;
+            break;
+        }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        FTS_CUDA(cudaKernelSetAttributeForDevice((cudaKernel_t)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, g_device));
+    }
+    for (auto& d : done)
+        if (d.first == fn) { d.second = smem; return FTS_OK; }
+    done.emplace_back(fn, smem);
+    return FTS_OK;
+}
+
 static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, void* args, cudaStream_t s)
 {
-    if (smem > 40 * 1024) {
-        if (smem > dyn_smem_limit())
-            return set_error(FTS_ERR_UNSUPPORTED, "level needs " + std::to_string(smem) + " B of shared memory per CTA (max " +
-                                                      std::to_string(dyn_smem_limit()) + ")");
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            FTS_CUDA(cudaKernelSetAttributeForDevice((cudaKernel_t)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, g_device));
-        }
-    }
+    if (int rc = ensure_dyn_smem(fn, smem)) return rc;
     void* params[] = {args};
     FTS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(block), params, smem, s));
+    g_launches.fetch_add(1);
+    return FTS_OK;
+}
+
+// Second kernel of a two-kernel call (the queue passes k_adaptive1d_tail / k_adaptive2d_cta): launched with
+// programmatic stream serialisation, so its CTAs are set up while the first kernel's last wave still runs
+// and wait in `griddepcontrol.wait` for the first kernel's completion and memory flush — the launch
+// latency of the second kernel (4-8 us on an idle stream) disappears behind the first.
+static int launch_dependent(const void* fn, unsigned grid, int block, size_t smem, void* args, cudaStream_t s)
+{
+    static const bool use_pdl = [] { const char* e = getenv("FTS_B200_PDL"); return !e || atoi(e) != 0; }();
+    if (!use_pdl) return launch_raw(fn, grid, block, smem, args, s);
+    if (int rc = ensure_dyn_smem(fn, smem)) return rc;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    void* params[] = {args};
+    FTS_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
     g_launches.fetch_add(1);
     return FTS_OK;
 }
@@ -678,14 +759,7 @@ static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, voi
 // one cluster of `csize` CTAs (thread-block cluster, distributed shared memory) per work item
 static int launch_cluster(const void* fn, unsigned nclusters, unsigned csize, int block, size_t smem, void* args, cudaStream_t s)
 {
-    if (smem > 40 * 1024) {
-        if (smem > dyn_smem_limit()) return set_error(FTS_ERR_UNSUPPORTED, "launch needs more shared memory than a CTA has");
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            FTS_CUDA(cudaKernelSetAttributeForDevice((cudaKernel_t)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, g_device));
-        }
-    }
+    if (int rc = ensure_dyn_smem(fn, smem)) return rc;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(nclusters * csize);
@@ -821,22 +895,63 @@ extern "C" int fts_integrate_batch_dev(fts_tables t, fts_integrand f, int order,
     return set_error(FTS_ERR_INTERNAL, "bad dtype");
 }
 
+// f(x_b) for a batch of points: pointwise values of a 1D integrand (host buffers; synchronous)
+template <class T> static int run_eval(const void* fn, fts_integrand f, const void* x, const void* params, int pstride, long long n, void* out)
+{
+    HostCtx* hc = nullptr;
+    if (int rc = host_ctx(&hc)) return rc;
+    cudaStream_t g_stream = hc->stream;  // this thread's stream
+    const size_t np = f->nparams ? (pstride ? (size_t)n * pstride : (size_t)f->nparams) : 0;
+    T *dx = nullptr, *dp = nullptr, *dv = nullptr;
+    FTS_CUDA(cudaMalloc((void**)&dx, sizeof(T) * n));
+    cudaError_t e = cudaMalloc((void**)&dv, sizeof(T) * n);
+    if (e == cudaSuccess && np) e = cudaMalloc((void**)&dp, sizeof(T) * np);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, sizeof(T) * n, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess && np) e = cudaMemcpyAsync(dp, params, sizeof(T) * np, cudaMemcpyHostToDevice, g_stream);
+    int rc = FTS_OK;
+    if (e == cudaSuccess) {
+        fts::Args<T> a;
+        memset(&a, 0, sizeof a);
+        a.low = dx; a.up = dx; a.bstride = 1; a.params = dp; a.pstride = pstride; a.batch = n; a.value = dv;
+        rc = launch(fn, n, 256, &a, g_stream);
+        if (rc == FTS_OK) e = cudaMemcpyAsync(out, dv, sizeof(T) * n, cudaMemcpyDeviceToHost, g_stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    cudaFree(dx); cudaFree(dv); cudaFree(dp);
+    if (rc) return rc;
+    FTS_CUDA(e);
+    return FTS_OK;
+}
+
+extern "C" int fts_eval_batch(fts_integrand f, int dtype, const void* x, const void* params, int params_stride, int64_t n, void* out_value)
+{
+    if (!f || !x || (n > 0 && !out_value) || n < 0) return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_eval_batch: bad arguments");
+    if (f->kind != FTS_KIND_1D) return set_error(FTS_ERR_UNSUPPORTED, "fts_eval_batch: integrands of kind f(x) only");
+    if (dtype != FTS_F32 && dtype != FTS_F64) return set_error(FTS_ERR_UNSUPPORTED, "fts_eval_batch: f32/f64");
+    if (f->nparams > 0 && (!params || (params_stride != 0 && params_stride < f->nparams))) return set_error(FTS_ERR_INVALID_ARGUMENT, "integrand needs " + std::to_string(f->nparams) + " parameters per point");
+    if (int rc = ensure_init()) return rc;
+    if (n == 0) return FTS_OK;
+    const void* fn = integrand_kernel(f, dtype, KID_EVAL, 1);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no pointwise-evaluation kernel for this integrand/dtype");
+    return dtype == FTS_F32 ? run_eval<float>(fn, f, x, params, params_stride, n, out_value) : run_eval<double>(fn, f, x, params, params_stride, n, out_value);
+}
+
 // host <-> device staging for the host-buffer entry points
-static int stage_in(int slot, const void* host, size_t bytes, void** dev)
+static int stage_in(HostCtx* hc, int slot, const void* host, size_t bytes, void** dev)
 {
     *dev = nullptr;
     if (!host || bytes == 0) return FTS_OK;
-    FTS_CUDA(g_scratch[slot].need(bytes));
-    FTS_CUDA(cudaMemcpyAsync(g_scratch[slot].p, host, bytes, cudaMemcpyHostToDevice, g_stream));
-    *dev = g_scratch[slot].p;
+    FTS_CUDA(hc->scratch[slot].need(bytes));
+    FTS_CUDA(cudaMemcpyAsync(hc->scratch[slot].p, host, bytes, cudaMemcpyHostToDevice, hc->stream));
+    *dev = hc->scratch[slot].p;
     return FTS_OK;
 }
-static int stage_out(int slot, bool wanted, size_t bytes, void** dev)
+static int stage_out(HostCtx* hc, int slot, bool wanted, size_t bytes, void** dev)
 {
     *dev = nullptr;
     if (!wanted || bytes == 0) return FTS_OK;
-    FTS_CUDA(g_scratch[slot].need(bytes));
-    *dev = g_scratch[slot].p;
+    FTS_CUDA(hc->scratch[slot].need(bytes));
+    *dev = hc->scratch[slot].p;
     return FTS_OK;
 }
 
@@ -844,7 +959,9 @@ extern "C" int fts_integrate_batch(fts_tables t, fts_integrand f, int order, con
                                    const void* params, int params_stride, int64_t batch, void* out_value)
 {
     if (int rc = check_fixed(t, f, order, low, up, bounds_stride, params, params_stride, batch, out_value)) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
+    HostCtx* hc = nullptr;
+    if (int rc = host_ctx(&hc)) return rc;
+    cudaStream_t g_stream = hc->stream;  // this thread's stream
     const size_t es = dtype_size(t->dtype);
     const int dim = kind_dim(f->kind);
     const size_t nb = bounds_stride ? (size_t)batch * bounds_stride : (size_t)dim;
@@ -856,13 +973,65 @@ extern "C" int fts_integrate_batch(fts_tables t, fts_integrand f, int order, con
     if (batch > 0 && np && params_stride && input_in_place()) dp = mapped_dev_ptr(params);
     if (batch > 0 && output_in_place()) dv = mapped_dev_ptr(out_value);
     const bool out_in_place = dv != nullptr;
-    if (!dl) if (int rc = stage_in(S_LOW, low, nb * es, &dl)) return rc;
-    if (!du) if (int rc = stage_in(S_UP, up, nb * es, &du)) return rc;
-    if (!dp) if (int rc = stage_in(S_PAR, params, np * es, &dp)) return rc;
-    if (!dv) if (int rc = stage_out(S_VAL, true, (size_t)batch * es, &dv)) return rc;
+    if (!dl) if (int rc = stage_in(hc, S_LOW, low, nb * es, &dl)) return rc;
+    if (!du) if (int rc = stage_in(hc, S_UP, up, nb * es, &du)) return rc;
+    if (!dp) if (int rc = stage_in(hc, S_PAR, params, np * es, &dp)) return rc;
+    if (!dv) if (int rc = stage_out(hc, S_VAL, true, (size_t)batch * es, &dv)) return rc;
     if (int rc = fts_integrate_batch_dev(t, f, order, dl, du, bounds_stride, dp, params_stride, batch, dv, g_stream)) return rc;
     if (batch && !out_in_place) FTS_CUDA(cudaMemcpyAsync(out_value, dv, (size_t)batch * es, cudaMemcpyDeviceToHost, g_stream));
     FTS_CUDA(cudaStreamSynchronize(g_stream));
+    return FTS_OK;
+}
+
+// integrate1D_cmpl(T, f, N) (integrate1D.jl:49-65): f(x, 1-x, 1+x) over [-1, 1] on the fixed grid, one
+// integral per parameter row
+template <class T> static int run_fixed_cmpl(const void* fn, fts_tables t, const void* params, int pstride, long long batch, void* out, cudaStream_t s)
+{
+    fts::Args<T> a;
+    memset(&a, 0, sizeof a);
+    a.grid = (const fts::Node<T>*)t->d_grid;
+    a.n = t->n;
+    a.h = load_elem<T>(t->h);
+    a.params = (const T*)params; a.pstride = pstride; a.batch = batch; a.value = (T*)out;
+    return launch(fn, batch, 256, &a, s);
+}
+
+static int check_fixed_cmpl(fts_tables t, fts_integrand f, int order, const void* params, int pstride, long long batch, void* out)
+{
+    if (!t || !f) return set_error(FTS_ERR_INVALID_ARGUMENT, "null handle");
+    if (f->kind != FTS_KIND_1D_CMPL) return set_error(FTS_ERR_DIMENSION_MISMATCH, "integrate1D_cmpl needs an integrand of kind f(x, bmx, xma)");
+    if (t->dtype == FTS_DD64) return set_error(FTS_ERR_UNSUPPORTED, "integrate1D_cmpl: f32/f64");
+    if (f->nparams > 0 && (!params || (pstride != 0 && pstride < f->nparams))) return set_error(FTS_ERR_INVALID_ARGUMENT, "integrand needs " + std::to_string(f->nparams) + " parameters per integral");
+    if (batch < 0 || (batch > 0 && !out)) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    if (order != FTS_ORDER_REFERENCE && order != FTS_ORDER_FAST && order != FTS_ORDER_AUTO) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad order");
+    return ensure_init();
+}
+
+extern "C" int fts_integrate1d_cmpl_batch_dev(fts_tables t, fts_integrand f, int order, const void* params, int params_stride, int64_t batch,
+                                              void* out_value, void* stream)
+{
+    if (int rc = check_fixed_cmpl(t, f, order, params, params_stride, batch, out_value)) return rc;
+    if (batch == 0) return FTS_OK;
+    const void* fn = integrand_kernel(f, t->dtype, KID_FIXED_CMPL, order == FTS_ORDER_FAST ? 1 : 0);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no integrate1D_cmpl kernel for this integrand/dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    return t->dtype == FTS_F32 ? run_fixed_cmpl<float>(fn, t, params, params_stride, batch, out_value, s)
+                               : run_fixed_cmpl<double>(fn, t, params, params_stride, batch, out_value, s);
+}
+
+extern "C" int fts_integrate1d_cmpl_batch(fts_tables t, fts_integrand f, int order, const void* params, int params_stride, int64_t batch, void* out_value)
+{
+    if (int rc = check_fixed_cmpl(t, f, order, params, params_stride, batch, out_value)) return rc;
+    HostCtx* hc = nullptr;
+    if (int rc = host_ctx(&hc)) return rc;
+    const size_t es = dtype_size(t->dtype);
+    const size_t np = f->nparams ? (params_stride ? (size_t)batch * params_stride : (size_t)f->nparams) : 0;
+    void *dp = nullptr, *dv = nullptr;
+    if (int rc = stage_in(hc, S_PAR, params, np * es, &dp)) return rc;
+    if (int rc = stage_out(hc, S_VAL, true, (size_t)batch * es, &dv)) return rc;
+    if (int rc = fts_integrate1d_cmpl_batch_dev(t, f, order, dp, params_stride, batch, dv, hc->stream)) return rc;
+    if (batch) FTS_CUDA(cudaMemcpyAsync(out_value, dv, (size_t)batch * es, cudaMemcpyDeviceToHost, hc->stream));
+    FTS_CUDA(cudaStreamSynchronize(hc->stream));
     return FTS_OK;
 }
 
@@ -913,9 +1082,9 @@ static int launch_level(const void* fn, fts_cache c, int dim, bool cmpl, const T
     return launch_raw(fn, grid_level_blocks(dim, level, nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s);
 }
 
-template <class T, int D> static void launch_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks, const T* partials, T* state, cudaStream_t s, int options = 0)
+template <class T, int D> static void launch_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks, const T* partials, T* state, cudaStream_t s, int options = 0, int max_levels = 0)
 {
-    fts::k_sharded_step<T, D><<<1, 1, 0, s>>>(low, up, tm, rtol, atol, level, nranks, partials, state, options);
+    fts::k_sharded_step<T, D><<<1, 1, 0, s>>>(low, up, tm, rtol, atol, level, nranks, partials, state, options, max_levels);
     g_launches.fetch_add(1);
 }
 
@@ -944,8 +1113,8 @@ static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int o
         const T* pp = params ? params + b * pstride : nullptr;
         for (int level = 0; level <= max_levels; ++level) {
             if (int rc = launch_level<T>(fn, c, dim, cmpl, lo, hi, pp, level, 0, 1, block_partials, ticket, partial, level ? state : nullptr, s)) return rc;
-            if (dim == 3) launch_step<T, 3>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options);
-            else launch_step<T, 2>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options);
+            if (dim == 3) launch_step<T, 3>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options, max_levels);
+            else launch_step<T, 2>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options, max_levels);
         }
         if (dim == 3) k_state_to_result<T, 3><<<1, 1, 0, s>>>(state, lo, hi, max_levels, options, out_value + b, out_err ? out_err + b : nullptr,
                                                               out_levels ? out_levels + b : nullptr, out_flags ? out_flags + b : nullptr);
@@ -1016,7 +1185,9 @@ static Style adaptive_style(fts_cache c, fts_integrand f, int order, int max_lev
     const void* fn_cta = is_dd ? nullptr : integrand_kernel(f, c->dtype, KID_ADAPT_CTA, 1);
     const void* fn_grid = (is_dd || dim == 1) ? nullptr : integrand_kernel(f, c->dtype, KID_LEVEL_GRID, 1);
     const size_t nmax = max_levels > 0 ? ((size_t)2 << max_levels) : 2;
-    const size_t smem_cta = dim == 1 ? 0 : (dim == 3 ? fts::SM3_ARRAYS : (cmpl ? 9 : 5)) * nmax * es;
+    // 2D: derived coordinate arrays + two raw node slices + two mbarriers (fts::sm2_group_bytes)
+    const size_t node_b = (cmpl ? 4 : 2) * es;
+    const size_t smem_cta = dim == 1 ? 0 : (dim == 3 ? fts::SM3_ARRAYS * nmax * es : (cmpl ? 9 : 5) * nmax * es + 2 * nmax * node_b + 16);
     const bool cta_ok = fn_cta && smem_cta <= dyn_smem_limit();
     const bool grid_ok = fn_grid && grid_level_smem(dim, cmpl, max_levels, es) <= dyn_smem_limit();
     if (fn_cta_out) *fn_cta_out = fn_cta;
@@ -1053,11 +1224,15 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
         // 2D batches large enough to fill the GPU with warps: one WARP per integral up to level
         // `lw` (no CTA barriers; shallow integrals such as config C stop at level 4), the rest is
         // queued and finished by whole CTAs in a second launch of the same kernel
-        static const int kWarpLevels = [] { const char* e = getenv("FTS_B200_WARP2D_LEVELS"); const int v = e ? atoi(e) : 5; return v < 0 ? -1 : (v > 7 ? 7 : v); }();
-        if (dim == 2 && kWarpLevels >= 0 && batch >= 8LL * g_prop.multiProcessorCount) {
+        // default 4: 4.4 KiB of shared memory per warp, seven 4-warp CTAs per SM — 4096 integrals are ONE wave
+        static const int kWarpLevels = [] { const char* e = getenv("FTS_B200_WARP2D_LEVELS"); const int v = e ? atoi(e) : 4; return v < 0 ? -1 : (v > 7 ? 7 : v); }();
+        const void* fn_warp = (dim == 2 && kWarpLevels >= 0 && batch >= 8LL * g_prop.multiProcessorCount) ? integrand_kernel(f, c->dtype, KID_ADAPT_WARP, 1) : nullptr;
+        if (dim == 2 && kWarpLevels >= 0 && !fn_warp) g_last_error.clear();
+        if (fn_warp) {
             const int lw = max_levels < kWarpLevels ? max_levels : kWarpLevels;
-            const int warps = fts::CTA_THREADS / 32;
-            const size_t smem_w = (size_t)warps * (cmpl ? 9 : 5) * ((size_t)2 << lw) * sizeof(T);
+            const int warps = fts::WARP2D_WARPS;
+            const size_t ncap_w = (size_t)2 << lw;
+            const size_t smem_w = (size_t)warps * ((cmpl ? 9 : 5) * ncap_w * sizeof(T) + 2 * ncap_w * (cmpl ? 4 : 2) * sizeof(T) + 16);
             int* queue = nullptr;
             if (int rc = tail_queue_for(s, (size_t)batch, &queue)) return rc;
             a.tail_count = queue;
@@ -1065,12 +1240,14 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
             a.tail_idx = queue + 2;
             a.group = 32;
             a.level = lw;
-            if (int rc = launch_raw(fn_cta, (unsigned)((batch + warps - 1) / warps), fts::CTA_THREADS, smem_w, &a, s)) return rc;
+            if (int rc = launch_raw(fn_warp, (unsigned)((batch + warps - 1) / warps), warps * 32, smem_w, &a, s)) return rc;
             if (lw == max_levels) return FTS_OK;  // nothing can be queued
+            // second pass: whole CTAs walk the queue of deeper integrals.  Two CTAs per SM: with an empty queue
+            // (every integral converged in the warp pass) the launch is over in a couple of microseconds
             a.group = 0;
             a.level = 0;
-            const long long cap = (long long)g_prop.multiProcessorCount * 8;
-            return launch_raw(fn_cta, (unsigned)(batch < cap ? batch : cap), fts::CTA_THREADS, smem_cta, &a, s);
+            const long long cap = (long long)g_prop.multiProcessorCount * 2;
+            return launch_dependent(fn_cta, (unsigned)(batch < cap ? batch : cap), fts::CTA_THREADS, smem_cta, &a, s);
         }
         return launch_raw(fn_cta, (unsigned)batch, fts::CTA_THREADS, smem_cta, &a, s);
     }
@@ -1112,7 +1289,7 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     if (int rc = launch(fn, batch, tpi_block(dim, c->dtype), &a, s)) return rc;
     if (fn_tail) {
         const long long cap = (long long)g_prop.multiProcessorCount * 8;
-        if (int rc = launch_raw(fn_tail, (unsigned)(batch < cap ? batch : cap), 256, 0, &a, s)) return rc;
+        if (int rc = launch_dependent(fn_tail, (unsigned)(batch < cap ? batch : cap), 256, 0, &a, s)) return rc;
     }
     return FTS_OK;
 }
@@ -1167,7 +1344,12 @@ extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int o
                                   int max_levels, int64_t batch, void* out_value, void* out_err, int32_t* out_levels, int32_t* out_flags)
 {
     if (int rc = check_adaptive(c, f, order, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value)) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
+    HostCtx* hc = nullptr;
+    if (int rc = host_ctx(&hc)) return rc;
+    cudaStream_t g_stream = hc->stream;  // this thread's stream, pipeline streams and scratch
+    cudaStream_t* g_pipe = hc->pipe;
+    cudaEvent_t g_pipe_ev = hc->ev;
+    Scratch* g_scratch = hc->scratch;
     const size_t es = dtype_size(c->dtype);
     const int dim = kind_dim(f->kind);
     const size_t nb = bounds_stride ? (size_t)batch * bounds_stride : (size_t)dim;
@@ -1371,12 +1553,12 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
         }
         if (int rc = launch_raw(fn, grid_level_blocks(dim, level, a.nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s)) return rc;
         if (shard) {
-            if (dim == 3) fts::k_sharded_step_fused<T, 3><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait);
-            else fts::k_sharded_step_fused<T, 2><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait);
+            if (dim == 3) fts::k_sharded_step_fused<T, 3><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait, max_levels);
+            else fts::k_sharded_step_fused<T, 2><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait, max_levels);
             g_launches.fetch_add(1);
         } else {
-            if (dim == 3) launch_step<T, 3>(low, up, tm, rtol, atol, level, 1, partial, state, s, options);
-            else launch_step<T, 2>(low, up, tm, rtol, atol, level, 1, partial, state, s, options);
+            if (dim == 3) launch_step<T, 3>(low, up, tm, rtol, atol, level, 1, partial, state, s, options, max_levels);
+            else launch_step<T, 2>(low, up, tm, rtol, atol, level, 1, partial, state, s, options, max_levels);
         }
     }
     FTS_CUDA(cudaGetLastError());
@@ -1387,6 +1569,13 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
 extern "C" int fts_adaptive_sharded_fused_dev(fts_cache c, fts_integrand f, const void* low, const void* up, const void* params,
                                               const void* rtol, const void* atol, int max_levels, int shard_from_level, int rank, int nranks,
                                               void* const* mailboxes, uint64_t epoch, void* state_dev, void* stream)
+{
+    return fts_adaptive_sharded_fused_opts_dev(c, f, low, up, params, rtol, atol, max_levels, shard_from_level, rank, nranks, mailboxes, epoch, state_dev, 0, stream);
+}
+
+extern "C" int fts_adaptive_sharded_fused_opts_dev(fts_cache c, fts_integrand f, const void* low, const void* up, const void* params,
+                                                   const void* rtol, const void* atol, int max_levels, int shard_from_level, int rank, int nranks,
+                                                   void* const* mailboxes, uint64_t epoch, void* state_dev, int options, void* stream)
 {
     if (!c || !f || !low || !up || !rtol || !atol || !state_dev) return set_error(FTS_ERR_INVALID_ARGUMENT, "sharded fused: null argument");
     if (int rc = check_cache_match(c, f)) return rc;
@@ -1400,26 +1589,32 @@ extern "C" int fts_adaptive_sharded_fused_dev(fts_cache c, fts_integrand f, cons
     cudaStream_t s = (cudaStream_t)stream;
     if (c->dtype == FTS_F64)
         return sharded_fused<double>(c, f, (const double*)low, (const double*)up, (const double*)params, load_elem<double>(rtol), load_elem<double>(atol),
-                                     max_levels, shard_from_level, rank, nranks, mailboxes, (double)epoch, (double*)state_dev, 0, s);
+                                     max_levels, shard_from_level, rank, nranks, mailboxes, (double)epoch, (double*)state_dev, options, s);
     if (c->dtype == FTS_F32)
         return sharded_fused<float>(c, f, (const float*)low, (const float*)up, (const float*)params, load_elem<float>(rtol), load_elem<float>(atol),
-                                    max_levels, shard_from_level, rank, nranks, mailboxes, (double)epoch, (float*)state_dev, 0, s);
+                                    max_levels, shard_from_level, rank, nranks, mailboxes, (double)epoch, (float*)state_dev, options, s);
     return set_error(FTS_ERR_UNSUPPORTED, "sharded fused: f32/f64 only");
 }
 
 extern "C" int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up, const void* rtol, const void* atol, int level,
                                              int nranks, const void* partials_dev, void* state_dev, void* stream)
 {
+    return fts_adaptive_sharded_step_opts_dev(c, low, up, rtol, atol, level, nranks, partials_dev, state_dev, 0, 0, stream);
+}
+
+extern "C" int fts_adaptive_sharded_step_opts_dev(fts_cache c, const void* low, const void* up, const void* rtol, const void* atol, int level,
+                                                  int nranks, const void* partials_dev, void* state_dev, int options, int max_levels, void* stream)
+{
     if (!c || !low || !up || !rtol || !atol || !partials_dev || !state_dev) return set_error(FTS_ERR_INVALID_ARGUMENT, "sharded step: null argument");
     if (c->D != 2 && c->D != 3) return set_error(FTS_ERR_UNSUPPORTED, "sharded step needs a tensor cache");
     if (int rc = ensure_init()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (c->dtype == FTS_F64) {
-        if (c->D == 3) launch_step<double, 3>((const double*)low, (const double*)up, load_elem<double>(c->tm), load_elem<double>(rtol), load_elem<double>(atol), level, nranks, (const double*)partials_dev, (double*)state_dev, s);
-        else launch_step<double, 2>((const double*)low, (const double*)up, load_elem<double>(c->tm), load_elem<double>(rtol), load_elem<double>(atol), level, nranks, (const double*)partials_dev, (double*)state_dev, s);
+        if (c->D == 3) launch_step<double, 3>((const double*)low, (const double*)up, load_elem<double>(c->tm), load_elem<double>(rtol), load_elem<double>(atol), level, nranks, (const double*)partials_dev, (double*)state_dev, s, options, max_levels);
+        else launch_step<double, 2>((const double*)low, (const double*)up, load_elem<double>(c->tm), load_elem<double>(rtol), load_elem<double>(atol), level, nranks, (const double*)partials_dev, (double*)state_dev, s, options, max_levels);
     } else if (c->dtype == FTS_F32) {
-        if (c->D == 3) launch_step<float, 3>((const float*)low, (const float*)up, load_elem<float>(c->tm), load_elem<float>(rtol), load_elem<float>(atol), level, nranks, (const float*)partials_dev, (float*)state_dev, s);
-        else launch_step<float, 2>((const float*)low, (const float*)up, load_elem<float>(c->tm), load_elem<float>(rtol), load_elem<float>(atol), level, nranks, (const float*)partials_dev, (float*)state_dev, s);
+        if (c->D == 3) launch_step<float, 3>((const float*)low, (const float*)up, load_elem<float>(c->tm), load_elem<float>(rtol), load_elem<float>(atol), level, nranks, (const float*)partials_dev, (float*)state_dev, s, options, max_levels);
+        else launch_step<float, 2>((const float*)low, (const float*)up, load_elem<float>(c->tm), load_elem<float>(rtol), load_elem<float>(atol), level, nranks, (const float*)partials_dev, (float*)state_dev, s, options, max_levels);
     } else {
         return set_error(FTS_ERR_UNSUPPORTED, "sharded step: f32/f64 only");
     }

@@ -26,6 +26,24 @@ struct Registrar {
     };                                                                                                       \
     static fts_host::Registrar k_reg_##FUNCTOR(k_entries_##FUNCTOR, 8);
 
+// pointwise evaluation of a 1D family (fts_eval_batch), f32 + f64
+#define FTS_REGISTER_EVAL(FAM, FUNCTOR)                                                                  \
+    static const fts_host::KernelEntry k_eval_entries_##FUNCTOR[] = {                                   \
+        {FAM, FTS_F32, fts_host::KID_EVAL, 1, FTS_KPTR(fts::k_eval1d<float, fts::FUNCTOR>)},            \
+        {FAM, FTS_F64, fts_host::KID_EVAL, 1, FTS_KPTR(fts::k_eval1d<double, fts::FUNCTOR>)},           \
+    };                                                                                                   \
+    static fts_host::Registrar k_eval_reg_##FUNCTOR(k_eval_entries_##FUNCTOR, 2);
+
+// integrate1D_cmpl of a complement family, f32 + f64, reference order and FAST
+#define FTS_REGISTER_FIXED_CMPL(FAM, FUNCTOR)                                                                     \
+    static const fts_host::KernelEntry k_fc_entries_##FUNCTOR[] = {                                              \
+        {FAM, FTS_F32, fts_host::KID_FIXED_CMPL, 0, FTS_KPTR(fts::k_fixed1d_cmpl_tpi<float, fts::FUNCTOR, false>)},  \
+        {FAM, FTS_F32, fts_host::KID_FIXED_CMPL, 1, FTS_KPTR(fts::k_fixed1d_cmpl_tpi<float, fts::FUNCTOR, true>)},   \
+        {FAM, FTS_F64, fts_host::KID_FIXED_CMPL, 0, FTS_KPTR(fts::k_fixed1d_cmpl_tpi<double, fts::FUNCTOR, false>)}, \
+        {FAM, FTS_F64, fts_host::KID_FIXED_CMPL, 1, FTS_KPTR(fts::k_fixed1d_cmpl_tpi<double, fts::FUNCTOR, true>)},  \
+    };                                                                                                            \
+    static fts_host::Registrar k_fc_reg_##FUNCTOR(k_fc_entries_##FUNCTOR, 4);
+
 // deep-level tail kernels of the 1D thread-per-integral path (CMPL selects the complement form)
 #define FTS_REGISTER_TAIL(FAM, FUNCTOR, CMPL)                                                                        \
     static const fts_host::KernelEntry k_tail_entries_##FUNCTOR[] = {                                               \
@@ -80,6 +98,14 @@ struct Registrar {
         {FAM, FTS_F64, fts_host::KID_ADAPT_CTA, 1, FTS_KPTR(fts::ADAPT_K<double, fts::FUNCTOR>)},       \
     };                                                                                                   \
     static fts_host::Registrar k_cta_reg_##FUNCTOR(k_cta_entries_##FUNCTOR, 2);
+
+// warp-per-integral kernel of a 2D family (shallow levels of large batches), f32 + f64
+#define FTS_REGISTER_WARP2D(FAM, FUNCTOR)                                                                \
+    static const fts_host::KernelEntry k_w2_entries_##FUNCTOR[] = {                                     \
+        {FAM, FTS_F32, fts_host::KID_ADAPT_WARP, 1, FTS_KPTR(fts::k_adaptive2d_warp<float, fts::FUNCTOR>)},  \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_WARP, 1, FTS_KPTR(fts::k_adaptive2d_warp<double, fts::FUNCTOR>)}, \
+    };                                                                                                   \
+    static fts_host::Registrar k_w2_reg_##FUNCTOR(k_w2_entries_##FUNCTOR, 2);
 
 // one-level whole-grid kernels (single large integral / multi-GPU shards), f32 + f64
 #define FTS_REGISTER_GRID(FAM, FUNCTOR, D)                                                               \

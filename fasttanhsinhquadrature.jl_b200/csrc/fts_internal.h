@@ -20,7 +20,10 @@ enum KernelId : int {
     KID_ADAPT_TAIL = 5,    // k_adaptive1d_tail               deep levels of queued 1D integrals (reference order)
     KID_ADAPT_ORD = 6,     // k_adaptive{2,3}d_ord            CTA per integral, REFERENCE summation order (small 2D/3D batches)
     KID_FIXED_ORD = 7,     // k_fixed{2,3}d_ord               CTA per integral, REFERENCE order (small 2D/3D batches)
-    KID_COUNT = 8
+    KID_EVAL = 8,          // k_eval1d                        pointwise integrand values (1D kinds)
+    KID_FIXED_CMPL = 9,    // k_fixed1d_cmpl_tpi              integrate1D_cmpl (fixed grid, complement signature)
+    KID_ADAPT_WARP = 10,   // k_adaptive2d_warp               warp per integral, shallow levels (large 2D batches, FAST only)
+    KID_COUNT = 11
 };
 
 struct KernelEntry {

@@ -17,7 +17,9 @@
 
 namespace fts {
 
-enum : int { OPT_QUAD_EDGE = 1 };
+enum : int { OPT_QUAD_EDGE = 1, OPT_FORCE_DEPTH = 2 };
+// FTS_OPT_FORCE_DEPTH: the stop rule only counts at the last level
+__device__ __forceinline__ bool may_stop(int options, int level, int max_levels) { return !(options & OPT_FORCE_DEPTH) || level == max_levels; }
 enum : int { FLAG_CONVERGED = 1, FLAG_MAX_LEVELS = 2, FLAG_ZERO_WIDTH = 4, FLAG_FLIPPED = 8 };
 
 #ifndef FTS_MAX_RANKS
@@ -91,6 +93,28 @@ template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP
 // functor — NVRTC user bodies included — falls back to N scalar evaluations.
 template <class F, class = void> struct HasEvalN { static constexpr bool value = false; };
 template <class F> struct HasEvalN<F, decltype((void)F::HAS_EVALN)> { static constexpr bool value = F::HAS_EVALN; };
+// Families whose Float64 code reads a lookup table from SHARED memory declare it (USES_EXP_TAB:
+// fts_math.cuh exp_n with EXP_SMEM; USES_LOG_TAB: log_n); every kernel copies the tables it needs at
+// entry — family_tables_init contains a barrier, so it runs before any thread can leave.
+template <class T> struct IsF64 { static constexpr bool value = false; };
+template <> struct IsF64<double> { static constexpr bool value = true; };
+template <class F, class = void> struct DeclaresExpTab { static constexpr bool value = false; };
+template <class F> struct DeclaresExpTab<F, decltype((void)F::USES_EXP_TAB)> { static constexpr bool value = F::USES_EXP_TAB; };
+template <class F, class = void> struct DeclaresLogTab { static constexpr bool value = false; };
+template <class F> struct DeclaresLogTab<F, decltype((void)F::USES_LOG_TAB)> { static constexpr bool value = F::USES_LOG_TAB; };
+template <class T, class F> struct UsesExpTab { static constexpr bool value = DeclaresExpTab<F>::value && IsF64<T>::value; };
+template <class T, class F> struct UsesLogTab { static constexpr bool value = DeclaresLogTab<F>::value && IsF64<T>::value; };
+// programmatic dependent launch (see launch_dependent in fts_host.cu): the first kernel of a two-kernel call
+// lets its dependent be scheduled early, the dependent waits for the first kernel's completion and memory
+// flush before it reads the queue.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class T, class F> __device__ __forceinline__ void family_tables_init()
+{
+    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();
+    if constexpr (UsesLogTab<T, F>::value) log_tab_init();
+}
 
 template <class T, class F, bool FAST, int N, int MODE = 0> __device__ __forceinline__ void eval1d_n(const T (&x)[N], const T* p, T (&f)[N])
 {
@@ -122,6 +146,22 @@ __device__ __forceinline__ void eval3d_n(const T (&x)[N], const T (&y)[N], const
         for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], y[i], z[i], p);
     }
 }
+
+// 2D complement protocol: f(x, y, bmx, xma, dmy, ymc)
+template <class T, class F, bool FAST, int N>
+__device__ __forceinline__ void eval2dc_n(const T (&x)[N], const T (&y)[N], const T (&bmx)[N], const T (&xma)[N], const T (&dmy)[N], const T (&ymc)[N],
+                                          const T* p, T (&f)[N])
+{
+    if constexpr (HasEvalN<F>::value) {
+        F::template evaln<T, FAST, N, 0>(x, y, bmx, xma, dmy, ymc, p, f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = F::template eval<T, FAST>(x[i], y[i], bmx[i], xma[i], dmy[i], ymc[i], p);
+    }
+}
+// families that evaluate a run of cells along k with the work shared between them (see F3Log::cells_run)
+template <class F, class = void> struct HasCellsRun { static constexpr bool value = false; };
+template <class F> struct HasCellsRun<F, decltype((void)F::HAS_CELLS_RUN)> { static constexpr bool value = F::HAS_CELLS_RUN; };
 
 template <class T> __device__ __forceinline__ Node<T> ldg_node(const Node<T>* p) { return *p; }
 template <> __device__ __forceinline__ Node<double> ldg_node<double>(const Node<double>* p)
@@ -163,12 +203,25 @@ template <class T> __device__ __forceinline__ bool quad_edge_axis(T& lo, T& hi, 
     return true;
 }
 
+// Pointwise values of a 1D integrand, f(x_b) with FMA contraction (FAST arithmetic): lets a caller
+// check a builtin family or an NVRTC body on the device (tests hold the table-driven exp/log to their
+// ulp bounds with it).  x is passed in `low`.
+template <class T, class F> __global__ void __launch_bounds__(256) k_eval1d(const Args<T> a)
+{
+    family_tables_init<T, F>();
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    a.value[b] = F::template eval<T, true>(a.low[b], p);
+}
+
 // =================================================================== fixed grids, reference order
 // integrate1D(f, low, up, x, w, h)   /root/reference/src/integrate1D.jl:90-102
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_fixed1d_tpi(const Args<T> a)
 {
-    constexpr int MODE = (HasEvalN<F>::value && sizeof(T) == 8) ? EXP_SMEM : 0;   // dd has sizeof 16, float 4
-    if constexpr (MODE != 0) exp_tab_init();
+    constexpr int MODE = UsesExpTab<T, F>::value ? EXP_SMEM : 0;
+    family_tables_init<T, F>();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -204,9 +257,30 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
     a.value[b] = dx * a.h * s;
 }
 
+// integrate1D_cmpl(T, f, N)   /root/reference/src/integrate1D.jl:49-65: f(x, 1-x, 1+x) over [-1, 1] on the
+// fixed grid, the complements formed by subtraction (not complement-accurate, App. B.9); one thread
+// per parameter row
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_fixed1d_cmpl_tpi(const Args<T> a)
+{
+    family_tables_init<T, F>();
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T one = num<T>::one();
+    T s = num<T>::half_pi() * F::template eval<T, FAST>(num<T>::zero(), one, one, p);
+    for (int i = 0; i < a.n; ++i) {
+        const Node<T> nd = ldg_node(a.grid + i);
+        const T omx = one - nd.x, opx = one + nd.x;
+        s = muladd<T, FAST>(nd.w, F::template eval<T, FAST>(nd.x, omx, opx, p) + F::template eval<T, FAST>(-nd.x, opx, omx, p), s);
+    }
+    a.value[b] = a.h * s;
+}
+
 // integrate2D(f, low, up, x, w, h)   /root/reference/src/integrate2D.jl:91-124
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_fixed2d_tpi(const Args<T> a)
 {
+    family_tables_init<T, F>();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -245,6 +319,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
 // integrate3D(f, low, up, x, w, h)   /root/reference/src/integrate3D.jl:150-207
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_fixed3d_tpi(const Args<T> a)
 {
+    family_tables_init<T, F>();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -296,10 +371,6 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
 
 // =================================================================== adaptive, reference order
 // adaptive_integrate_1D typed core   /root/reference/src/adaptive.jl:28-75
-// compile-time helpers for the exp fast paths (fts_math.cuh): only Float64 uses the table
-template <class T> struct IsF64 { static constexpr bool value = false; };
-template <> struct IsF64<double> { static constexpr bool value = true; };
-template <class T, class F> struct UsesExpTab { static constexpr bool value = HasEvalN<F>::value && IsF64<T>::value; };
 
 // levels of one integral; MODE selects the exp variant (shared-memory table, no range test)
 template <class T, class F, bool FAST, int MODE>
@@ -360,7 +431,7 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
         err = fm::abs(new_res - old_res);
         level_used = level;
         old_res = new_res;
-        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+        if (err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels)) {
             flags |= FLAG_CONVERGED;
             break;
         }
@@ -376,7 +447,8 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
 
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_tpi(const Args<T> a)
 {
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // before any thread leaves (contains a barrier)
+    pdl_launch_dependents();     // the tail kernel may be set up behind this grid's last wave
+    family_tables_init<T, F>();  // before any thread leaves (contains a barrier)
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -408,6 +480,8 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2)
 // adaptive_integrate_1D_cmpl typed core   /root/reference/src/adaptive.jl:727-785
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_adaptive1d_cmpl_tpi(const Args<T> a)
 {
+    pdl_launch_dependents();
+    family_tables_init<T, F>();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -454,7 +528,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
         err = fm::abs(new_res - old_res);
         level_used = level;
         old_res = new_res;
-        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+        if (err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels)) {
             flags |= FLAG_CONVERGED;
             break;
         }
@@ -501,10 +575,12 @@ template <class T> __device__ __forceinline__ void ordered_add(T& s, const T* te
 // (Double64 tiles are tree-reduced instead, see below.)
 template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bounds__(256) k_adaptive1d_tail(const Args<T> a)
 {
+    family_tables_init<T, F>();
     constexpr int TILE = 1024;
     __shared__ T terms[TILE];
     __shared__ int s_done;
     const int tid = threadIdx.x;
+    pdl_wait_primary();  // the thread-per-integral kernel has completed: the queue is final and visible
     const int count = *a.tail_count;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         const long long b = a.tail_idx[q];
@@ -569,7 +645,7 @@ template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bound
                 err = fm::abs(new_res - old_res);
                 level_used = level;
                 old_res = new_res;
-                const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+                const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
                 if (conv) flags |= FLAG_CONVERGED;
                 s_done = conv ? 1 : 0;
             }
@@ -659,6 +735,7 @@ template <int D, class T> __device__ __forceinline__ bool load_box(const Args<T>
 // CMPL=true: tensor-complement extension on NodeC tables (BASELINE config C)
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_adaptive2d_tpi(const Args<T> a)
 {
+    family_tables_init<T, F>();
     constexpr bool CMPL = is_cmpl2d<F>::value;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
@@ -718,7 +795,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
         err = fm::abs(new_res - old_res);
         level_used = level;
         old_res = new_res;
-        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+        if (err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels)) {
             flags |= FLAG_CONVERGED;
             break;
         }
@@ -794,6 +871,7 @@ template <class T, class F, bool FAST> __device__ __forceinline__ T level0_3d(co
 // adaptive_integrate_3D typed core   /root/reference/src/adaptive.jl:352-471
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_adaptive3d_tpi(const Args<T> a)
 {
+    family_tables_init<T, F>();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     T p[F::NP > 0 ? F::NP : 1];
@@ -837,7 +915,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
         err = fm::abs(new_res - old_res);
         level_used = level;
         old_res = new_res;
-        if (err <= fm::err_target(new_res, a.rtol, a.atol)) {
+        if (err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels)) {
             flags |= FLAG_CONVERGED;
             break;
         }
@@ -966,6 +1044,7 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ T term2d(const
 // adaptive_integrate_2D typed core, reference order, one CTA per integral   adaptive.jl:154-224
 template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive2d_ord(const Args<T> a)
 {
+    family_tables_init<T, F>();
     constexpr bool CMPL = is_cmpl2d<F>::value;
     __shared__ int s_done;
     const long long b = cluster_id_x();  // one integral per cluster (of 1, 2, 4 or 8 CTAs)
@@ -1018,7 +1097,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive2d_
             err = fm::abs(new_res - old_res);
             level_used = level;
             old_res = new_res;
-            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
             if (conv) flags |= FLAG_CONVERGED;
             cluster_broadcast_int(&s_done, conv ? 1 : 0);
         }
@@ -1076,6 +1155,7 @@ template <class T, class F> __device__ __forceinline__ T term3d(const Args<T>& a
 // adaptive_integrate_3D typed core, reference order, one CTA per integral   adaptive.jl:352-471
 template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_ord(const Args<T> a)
 {
+    family_tables_init<T, F>();
     __shared__ int s_done;
     const long long b = cluster_id_x();  // one integral per cluster (of 1, 2, 4 or 8 CTAs)
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
@@ -1110,7 +1190,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
             err = fm::abs(new_res - old_res);
             level_used = level;
             old_res = new_res;
-            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
             if (conv) flags |= FLAG_CONVERGED;
             cluster_broadcast_int(&s_done, conv ? 1 : 0);
         }
@@ -1134,6 +1214,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_adaptive3d_
 // (cluster machinery of ordered_sum_cluster: one cluster of 1..8 CTAs per integral)
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed1d_ord(const Args<T> a)
 {
+    family_tables_init<T, F>();
     cluster_entry_sync();
     const long long b = cluster_id_x();
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
@@ -1156,6 +1237,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_fixed1d_ord
 // integrate2D: n axis terms, then n row terms w_i * (inner sum over j)
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord(const Args<T> a)
 {
+    family_tables_init<T, F>();
     cluster_entry_sync();
     const long long b = cluster_id_x();
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;
@@ -1196,6 +1278,7 @@ template <class T, class F> __global__ void __launch_bounds__(256) k_fixed2d_ord
 // integrate3D: n axis terms, then for every (i, j) its plane term followed by its octant row sum
 template <class T, class F> __global__ void __launch_bounds__(256) k_fixed3d_ord(const Args<T> a)
 {
+    family_tables_init<T, F>();
     cluster_entry_sync();
     const long long b = cluster_id_x();
     const bool adder = cluster_ctarank() == 0 && threadIdx.x == 0;

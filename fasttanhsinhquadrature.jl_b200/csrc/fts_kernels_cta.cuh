@@ -66,6 +66,7 @@ template <class T> __device__ __forceinline__ Comp<T> comp_of(T v)
 // adaptive_integrate_1D_avx / adaptive_integrate_1D_cmpl_avx   adaptive.jl:94-133, 805-855
 template <class T, class F, bool CMPL> __device__ __forceinline__ void adaptive1d_cta_body(const Args<T>& a)
 {
+    family_tables_init<T, F>();
     __shared__ T red[64];
     __shared__ int s_done;
     const long long b = blockIdx.x;
@@ -130,7 +131,7 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ void adaptive1
             err = fm::abs(new_res - old_res);
             old_res = new_res;
             level_used = level;
-            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
             if (conv) flags |= FLAG_CONVERGED;
             s_done = conv ? 1 : 0;
         }
@@ -149,6 +150,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
 // integrate1D_avx   integrate1D.jl:138-147
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed1d_cta(const Args<T> a)
 {
+    family_tables_init<T, F>();
     __shared__ T red[64];
     const long long b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -212,8 +214,12 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ T cell2(const 
     T f;
     if constexpr (CMPL) {
         const T bx = s.bx[i], ax = s.ax[i], dyc = s.dyc[j], cy = s.cy[j];
-        f = (F::template eval<T, true>(xp, yp, bx, ax, dyc, cy, p) + F::template eval<T, true>(xm, yp, ax, bx, dyc, cy, p)) +
-            (F::template eval<T, true>(xp, ym, bx, ax, cy, dyc, p) + F::template eval<T, true>(xm, ym, ax, bx, cy, dyc, p));
+        // the four reflections side by side (families with a batch evaluator interleave their chains)
+        const T xs[4] = {xp, xm, xp, xm}, ys[4] = {yp, yp, ym, ym};
+        const T b_[4] = {bx, ax, bx, ax}, a_[4] = {ax, bx, ax, bx}, d_[4] = {dyc, dyc, cy, cy}, c_[4] = {cy, cy, dyc, dyc};
+        T v[4];
+        eval2dc_n<T, F, true, 4>(xs, ys, b_, a_, d_, c_, p, v);
+        f = (v[0] + v[1]) + (v[2] + v[3]);
     } else if constexpr (HasEvalN<F>::value) {
         const T xs[4] = {xp, xm, xp, xm}, ys[4] = {yp, yp, ym, ym};
         T v[4];
@@ -272,7 +278,148 @@ __device__ __forceinline__ T level_sum_2d(const Sm2<T>& s, const T* p, int n, in
     return acc;
 }
 
+// ---- warp-shaped level sum: a lane owns a column ------------------------------------------------------
+// x-side arrays of the level through 32-bit shared-window addresses that the compiler must keep in
+// registers (`asm("" : "+r")`): left to itself it re-derives the nine array pointers from threadIdx and the
+// launch arguments in every trip of the cell loop (35 of 91 instructions per cell) rather than spend
+// registers under the 72-register bound that keeps 28 warps on an SM.
+template <class T> struct XSide { unsigned xp, xm, w, bx, ax; };
+__device__ __forceinline__ unsigned smem_addr_pinned(const void* p)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ double lds_elem(unsigned addr, double)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_elem(unsigned addr, float)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <class T, bool CMPL> __device__ __forceinline__ XSide<T> make_xside(const Sm2<T>& s)
+{
+    XSide<T> x;
+    x.xp = smem_addr_pinned(s.xp); x.xm = smem_addr_pinned(s.xm); x.w = smem_addr_pinned(s.w);
+    x.bx = CMPL ? smem_addr_pinned(s.bx) : 0u;
+    x.ax = CMPL ? smem_addr_pinned(s.ax) : 0u;
+    return x;
+}
+// One cell (i, j) of a column whose y-side values the lane keeps in registers: the 4 reflections are evaluated
+// side by side.  (Seven warps per scheduler are resident in the warp-shaped kernel: 4 chains per warp already
+// fill the FP64 pipe, and a second cell per trip costs the registers that keep 28 warps on an SM.)
+template <class T> struct Col2 { T yp, ym, dyc, cy, wj; };
+template <class T, class F, bool CMPL> __device__ __forceinline__ T cell_col(const XSide<T>& x, const T* p, const Col2<T>& c, unsigned off)
+{
+    T v[4];
+    if constexpr (CMPL) {
+        // complement families are functions of the distances: the plain coordinates are only fetched when the body reads them
+        const T bx = lds_elem(x.bx + off, T()), ax = lds_elem(x.ax + off, T());
+        const T xp = lds_elem(x.xp + off, T()), xm = lds_elem(x.xm + off, T());
+        const T xs[4] = {xp, xm, xp, xm}, ys[4] = {c.yp, c.yp, c.ym, c.ym};
+        const T b_[4] = {bx, ax, bx, ax}, a_[4] = {ax, bx, ax, bx}, d_[4] = {c.dyc, c.dyc, c.cy, c.cy}, c_[4] = {c.cy, c.cy, c.dyc, c.dyc};
+        eval2dc_n<T, F, true, 4>(xs, ys, b_, a_, d_, c_, p, v);
+    } else {
+        const T xp = lds_elem(x.xp + off, T()), xm = lds_elem(x.xm + off, T());
+        const T xs[4] = {xp, xm, xp, xm}, ys[4] = {c.yp, c.yp, c.ym, c.ym};
+        eval2d_n<T, F, true, 4, UsesExpTab<T, F>::value ? EXP_SMEM : 0>(xs, ys, p, v);
+    }
+    return (lds_elem(x.w + off, T()) * c.wj) * ((v[0] + v[1]) + (v[2] + v[3]));
+}
+template <class T, bool CMPL> __device__ __forceinline__ Col2<T> load_col(const Sm2<T>& s, int j)
+{
+    Col2<T> c;
+    c.yp = s.yp[j]; c.ym = s.ym[j]; c.wj = s.w[j];
+    if constexpr (CMPL) { c.dyc = s.dyc[j]; c.cy = s.cy[j]; }
+    else { c.dyc = num<T>::zero(); c.cy = num<T>::zero(); }
+    return c;
+}
+// New cells of a level for ONE WARP (0-based: rows i even -> every column, rows i odd -> even columns), n a
+// power of two >= 4: a lane owns a column j, keeps its y-side values in registers and walks down the rows —
+// the lanes of a row group read the same x-side entry (shared-memory broadcast), no flat-index decode per
+// cell.  Levels with fewer than 32 columns split the rows over 32/columns lane groups.
+template <class T, class F, bool CMPL> __device__ __forceinline__ T level_sum_2d_warp(const Sm2<T>& s, const T* p, int n, int lane)
+{
+    const XSide<T> x = make_xside<T, CMPL>(s);
+    const unsigned nbytes = (unsigned)n * (unsigned)sizeof(T);
+    T acc = num<T>::zero();
+    {   // even rows x all columns
+        const int cpl = n < 32 ? n : 32, sh = __ffs(cpl) - 1, g = 32 >> sh;  // columns per pass (a power of two), row groups
+        const unsigned off0 = (unsigned)(2 * (lane >> sh)) * (unsigned)sizeof(T), step = (unsigned)(2 * g) * (unsigned)sizeof(T);
+        for (int j = lane & (cpl - 1); j < n; j += 32) {
+            const Col2<T> c = load_col<T, CMPL>(s, j);
+#pragma unroll 1
+            for (unsigned off = off0; off < nbytes; off += step) acc = acc + cell_col<T, F, CMPL>(x, p, c, off);
+        }
+    }
+    {   // odd rows x even columns
+        const int half = n >> 1, cpl = half < 32 ? half : 32, sh = __ffs(cpl) - 1, g = 32 >> sh;
+        const unsigned off0 = (unsigned)(1 + 2 * (lane >> sh)) * (unsigned)sizeof(T), step = (unsigned)(2 * g) * (unsigned)sizeof(T);
+        for (int j = (lane & (cpl - 1)) << 1; j < n; j += 64) {
+            const Col2<T> c = load_col<T, CMPL>(s, j);
+#pragma unroll 1
+            for (unsigned off = off0; off < nbytes; off += step) acc = acc + cell_col<T, F, CMPL>(x, p, c, off);
+        }
+    }
+    for (int t = lane; t < (n >> 1); t += 32) acc = acc + axis2<T, F, CMPL>(s, p, t << 1);
+    return acc;
+}
+
 extern __shared__ __align__(16) unsigned char fts_dyn_smem[];
+
+// ---- bulk-async staging of a level's node slice (TMA unit: cp.async.bulk + mbarrier) -------------
+// The node slice of level l+1 ({x,w} or {x,w,c,pad} records, contiguous in the cache) is copied
+// global -> shared by the TMA unit WHILE the group evaluates level l: one elected thread posts the
+// expected byte count on an mbarrier and issues the copy, nobody waits for global memory inside the
+// level loop.  Two raw buffers and two barriers per group, used alternately; `use[b]` counts the
+// completed phases of barrier b (the mbarrier's phase bit is its parity).
+struct NodePipe {
+    unsigned bar[2];   // shared-window addresses of the two mbarriers
+    unsigned raw[2];   // shared-window addresses of the two raw slice buffers
+    unsigned use[2];   // waits done on each barrier (uniform over the group's threads)
+};
+__device__ __forceinline__ void pipe_init(NodePipe& np, void* bars, void* raw0, void* raw1, bool elected)
+{
+    np.bar[0] = (unsigned)__cvta_generic_to_shared(bars);
+    np.bar[1] = np.bar[0] + 8u;
+    np.raw[0] = (unsigned)__cvta_generic_to_shared(raw0);
+    np.raw[1] = (unsigned)__cvta_generic_to_shared(raw1);
+    np.use[0] = np.use[1] = 0u;
+    if (elected) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(np.bar[0]) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(np.bar[1]) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+// elected thread: post `bytes` on barrier b and start the copy of [src, src + bytes) into raw buffer b
+__device__ __forceinline__ void pipe_issue(const NodePipe& np, int b, const void* src, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(np.bar[b]), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(np.raw[b]), "l"(src), "r"(bytes),
+                 "r"(np.bar[b])
+                 : "memory");
+}
+// every thread of the group: wait until the copy posted on barrier b has landed
+__device__ __forceinline__ void pipe_wait(NodePipe& np, int b)
+{
+    const unsigned parity = np.use[b] & 1u;
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(np.bar[b]), "r"(parity) : "memory");
+    } while (!done);
+    np.use[b] += 1u;
+}
+template <class T, bool CMPL> __device__ __forceinline__ unsigned node_bytes() { return CMPL ? (unsigned)sizeof(NodeC<T>) : (unsigned)sizeof(Node<T>); }
+// shared memory of one group of the 2D adaptive kernel, in bytes: derived coordinate arrays + two raw slices + two barriers
+template <class T, bool CMPL> __host__ __device__ __forceinline__ size_t sm2_group_bytes(int ncap)
+{
+    return (size_t)(CMPL ? 9 : 5) * ncap * sizeof(T) + 2 * (size_t)ncap * (CMPL ? sizeof(NodeC<T>) : sizeof(Node<T>)) + 16;
+}
 
 // A "group" of G threads owns one integral: the whole CTA (G = CTA_THREADS) or one warp (G = 32).
 template <int G> __device__ __forceinline__ void group_sync()
@@ -282,8 +429,17 @@ template <int G> __device__ __forceinline__ void group_sync()
 }
 template <class T, int G> __device__ __forceinline__ Comp<T> group_reduce(Comp<T> v, T* red)  // valid in the group's thread 0
 {
-    if constexpr (G == 32) return warp_reduce(v);
-    else return block_reduce(v, red);
+    if constexpr (G == 32) {
+        // one warp = 32 partial sums: a plain shuffle tree (5 roundings, ~5e-16) instead of the TwoSum merges of
+        // the CTA and grid reductions, which cost as many instructions per level as 5 cells; the running total
+        // over the levels stays compensated
+        T t = v.s + v.c;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t = t + __shfl_down_sync(0xffffffffu, t, off);
+        return comp_of(t);
+    } else {
+        return block_reduce(v, red);
+    }
 }
 
 // adaptive_integrate_2D_avx (+ tensor-complement extension)   adaptive.jl:242-333
@@ -292,7 +448,7 @@ template <class T, int G> __device__ __forceinline__ Comp<T> group_reduce(Comp<T
 // whole CTAs instead of going deeper here (the group's shared-memory slice holds 2^(level_cap+1)
 // nodes per array).
 template <class T, class F, int G>
-__device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, int gtid, T* smem, int ncap, int level_cap, T* red, int* s_done)
+__device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, int gtid, T* smem, int ncap, int level_cap, T* red, int* s_done, NodePipe& np)
 {
     constexpr bool CMPL = is_cmpl2d<F>::value;
     T p[F::NP > 0 ? F::NP : 1];
@@ -310,6 +466,16 @@ __device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, 
     s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
     s.w0 = num<T>::half_pi();
     sm2_carve<T, CMPL>(s, smem, ncap);
+    const unsigned char* raw_base = reinterpret_cast<const unsigned char*>(smem + sm2_elems<T, CMPL>(ncap));
+    const int deepest = a.max_levels < level_cap ? a.max_levels : level_cap;  // deepest level this pass can reach
+    // node slice of `level` (n = 2^(level+1) records at offset n - 4) -> raw buffer level & 1, by the TMA unit
+    auto prefetch = [&](int level) {
+        if (gtid != 0 || level > deepest) return;
+        const int n = 2 << level;
+        const void* src = CMPL ? (const void*)(a.nodes_c + (n - 4)) : (const void*)(a.nodes + (n - 4));
+        pipe_issue(np, level & 1, src, (unsigned)n * node_bytes<T, CMPL>());
+    };
+    prefetch(1);  // in flight while level 0 is evaluated
     T h = a.tm * half;
     // level 0: base grid {h, 2h}, all cells new (adaptive.jl:264-272)
     sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2, gtid, G);
@@ -323,23 +489,33 @@ __device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, 
     T old_res = s.dx * s.dy * (h * h) * s_total.value();
     T err = num<T>::zero();
     int level_used = 0;
+    int in_flight = deepest >= 1 ? 1 : 0;  // level whose slice has been requested but not yet consumed (0: none)
+    bool queued = false;
     for (int level = 1; level <= a.max_levels; ++level) {
         if (level > level_cap) {  // too deep for this group's shared-memory slice: whole-CTA pass
             if (gtid == 0) a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
-            return;
+            queued = true;
+            break;
         }
         h = h * half;
         const int n = 2 << level;
         group_sync<G>();  // every thread is done with the previous level's coordinates
+        pipe_wait(np, level & 1);  // the slice of this level has landed in shared memory
+        in_flight = 0;
         if constexpr (CMPL) {
-            const NodeC<T>* lv = a.nodes_c + (n - 4);
+            const NodeC<T>* lv = reinterpret_cast<const NodeC<T>*>(raw_base + (size_t)(level & 1) * ncap * sizeof(NodeC<T>));
             sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n, gtid, G);
         } else {
-            const Node<T>* lv = a.nodes + (n - 4);
+            const Node<T>* lv = reinterpret_cast<const Node<T>*>(raw_base + (size_t)(level & 1) * ncap * sizeof(Node<T>));
             sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n, gtid, G);
         }
         group_sync<G>();
-        acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, false, gtid, G);
+        if (level + 1 <= deepest) {  // the other raw buffer was last read two levels ago: refill it during this level's evaluation
+            prefetch(level + 1);
+            in_flight = level + 1;
+        }
+        if (G == 32) acc = level_sum_2d_warp<T, F, CMPL>(s, p, n, gtid);
+        else acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, false, gtid, G);
         const Comp<T> lv_sum = group_reduce<T, G>(comp_of(acc), red);
         int done = 0;
         if (gtid == 0) {
@@ -348,7 +524,7 @@ __device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, 
             err = fm::abs(new_res - old_res);
             old_res = new_res;
             level_used = level;
-            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
             if (conv) flags |= FLAG_CONVERGED;
             done = conv ? 1 : 0;
         }
@@ -361,39 +537,61 @@ __device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, 
         }
         if (done) break;
     }
-    if (gtid == 0) {
+    // a slice requested for a level that is never evaluated (converged, or handed to the queue) is still
+    // consumed: the barrier's phase count stays in step for the group's next integral
+    if (in_flight) pipe_wait(np, in_flight & 1);
+    if (gtid == 0 && !queued) {
         if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
         store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
     }
 }
 
-// Launch shapes (Args::group): 0 = one CTA per integral (blockIdx = integral, or — with a queue in
-// a.tail_idx — the CTAs walk the queued integrals); 32 = one WARP per integral, levels <= a.level
-// (shallow integrals: 4 225 evaluations at level 4 keep 32 lanes busy without any CTA barrier;
-// config C 68 -> about 20 us), deeper ones are queued for a second launch in shape 0.
+// Launch shapes of the cooperative 2D adaptive path:
+//   k_adaptive2d_warp  one WARP per integral up to level a.level (shallow integrals: 4 225 evaluations at
+//                      level 4 keep 32 lanes busy without any CTA barrier); CTAs of 4 warps and at most 72
+//                      registers, so that 7 CTAs = 28 warps fit an SM and 4096 integrals run as ONE wave;
+//                      integrals that need deeper levels are queued (a.tail_idx)
+//   k_adaptive2d_cta   one CTA per integral: blockIdx = integral, or — with a queue in a.tail_idx —
+//                      the CTAs walk the queued integrals (second launch after k_adaptive2d_warp)
+constexpr int WARP2D_WARPS = 4;
+template <class T, class F> __global__ void __launch_bounds__(WARP2D_WARPS * 32, 7) k_adaptive2d_warp(const Args<T> a)
+{
+    pdl_launch_dependents();     // the queue pass (k_adaptive2d_cta) may be set up behind this grid
+    family_tables_init<T, F>();  // barrier inside: before any early return
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * WARP2D_WARPS + warp;
+    const int ncap = 2 << a.level;
+    unsigned char* mine = fts_dyn_smem + (size_t)warp * sm2_group_bytes<T, CMPL>(ncap);
+    unsigned char* raw0 = mine + sm2_elems<T, CMPL>(ncap) * sizeof(T);
+    NodePipe np;
+    pipe_init(np, raw0 + 2 * (size_t)ncap * node_bytes<T, CMPL>(), raw0, raw0 + (size_t)ncap * node_bytes<T, CMPL>(), lane == 0);
+    __syncwarp();
+    if (b >= a.batch) return;
+    adaptive2d_group<T, F, 32>(a, b, lane, reinterpret_cast<T*>(mine), ncap, a.level, nullptr, nullptr, np);
+}
+
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive2d_cta(const Args<T> a)
 {
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
+    family_tables_init<T, F>();  // barrier inside: before any early return
     constexpr bool CMPL = is_cmpl2d<F>::value;
     __shared__ T red[64];
     __shared__ int s_done;
-    T* smem = reinterpret_cast<T*>(fts_dyn_smem);
-    if (a.group == 32) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const long long b = (long long)blockIdx.x * (CTA_THREADS / 32) + warp;
-        if (b >= a.batch) return;
-        const int ncap = 2 << a.level;
-        adaptive2d_group<T, F, 32>(a, b, lane, smem + (size_t)warp * sm2_elems<T, CMPL>(ncap), ncap, a.level, nullptr, nullptr);
-        return;
-    }
+    unsigned char* dyn = fts_dyn_smem;
+    NodePipe np;
     const int nmax = a.max_levels > 0 ? (2 << a.max_levels) : 2;
+    T* smem = reinterpret_cast<T*>(dyn);
+    unsigned char* raw0 = dyn + sm2_elems<T, CMPL>(nmax) * sizeof(T);
+    pipe_init(np, raw0 + 2 * (size_t)nmax * node_bytes<T, CMPL>(), raw0, raw0 + (size_t)nmax * node_bytes<T, CMPL>(), threadIdx.x == 0);
+    __syncthreads();
     if (a.tail_idx == nullptr) {
-        adaptive2d_group<T, F, CTA_THREADS>(a, blockIdx.x, threadIdx.x, smem, nmax, a.max_levels, red, &s_done);
+        adaptive2d_group<T, F, CTA_THREADS>(a, blockIdx.x, threadIdx.x, smem, nmax, a.max_levels, red, &s_done, np);
         return;
     }
+    pdl_wait_primary();  // the warp pass has completed: the queue is final and visible
     const int count = *a.tail_count;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
-        adaptive2d_group<T, F, CTA_THREADS>(a, a.tail_idx[q], threadIdx.x, smem, nmax, a.max_levels, red, &s_done);
+        adaptive2d_group<T, F, CTA_THREADS>(a, a.tail_idx[q], threadIdx.x, smem, nmax, a.max_levels, red, &s_done, np);
         __syncthreads();
     }
     if (threadIdx.x == 0) {  // the last CTA to leave re-arms the queue (see k_adaptive1d_tail)
@@ -409,7 +607,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
 // integrate2D_avx   integrate2D.jl:46-73
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed2d_cta(const Args<T> a)
 {
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
+    family_tables_init<T, F>();  // barrier inside: before any early return
     __shared__ T red[64];
     const long long b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -493,11 +691,22 @@ template <class T, class F> __device__ __forceinline__ T cell3(const Sm3<T>& s, 
 template <class T, class F, int CH> __device__ __forceinline__ T cells3_run(const Sm3<T>& s, const T* p, int n, int i, int j, int k0, int kstep)
 {
     const T xp = s.xp[i], xm = s.xm[i], yp = s.yp[j], ym = s.ym[j];
+    if constexpr (HasCellsRun<F>::value) {
+        T zp[CH], zm[CH], wk[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int q = sm3_q(k0 + c * kstep, n);
+            zp[c] = s.zpq[q];
+            zm[c] = s.zmq[q];
+            wk[c] = s.wq[q];
+        }
+        return (s.w[i] * s.w[j]) * F::template cells_run<T, CH>(xp, xm, yp, ym, zp, zm, wk, p);
+    }
     T acc = num<T>::zero();
     // interleaved-batch integrands already keep 8 chains in flight per cell: unrolling the run as
     // well costs 30+ registers (156 -> 1 CTA/SM); everyone else is unrolled so that common
     // sub-expressions of the CH cells merge
-    constexpr int UNROLL = 1;
+    constexpr int UNROLL = HasEvalN<F>::value ? 1 : CH;
 #pragma unroll UNROLL
     for (int c = 0; c < CH; ++c) {
         const int q = sm3_q(k0 + c * kstep, n);
@@ -640,7 +849,7 @@ __device__ __forceinline__ T level_sum_3d(const Sm3<T>& s, const T* p, int n, in
 // adaptive_integrate_3D_avx   adaptive.jl:489-706
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive3d_cta(const Args<T> a)
 {
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
+    family_tables_init<T, F>();  // barrier inside: before any early return
     __shared__ T red[64];
     __shared__ int s_done;
     const long long b = blockIdx.x;
@@ -685,7 +894,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
             err = fm::abs(new_res - old_res);
             old_res = new_res;
             level_used = level;
-            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol);
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
             if (conv) flags |= FLAG_CONVERGED;
             s_done = conv ? 1 : 0;
         }
@@ -701,7 +910,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
 // integrate3D_avx   integrate3D.jl:68-123
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fixed3d_cta(const Args<T> a)
 {
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();  // barrier inside: before any early return
+    family_tables_init<T, F>();  // barrier inside: before any early return
     __shared__ T red[64];
     const long long b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -734,7 +943,7 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
     __shared__ T red[64];
     __shared__ int s_last;
     if (a.state && a.state[5] != num<T>::zero()) return;  // converged at an earlier level
-    if constexpr (UsesExpTab<T, F>::value) exp_tab_init();
+    family_tables_init<T, F>();
     const int tid = threadIdx.x;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, 0);
@@ -819,7 +1028,7 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
 // every later launch of the call exits.
 template <class T, int D> __global__ void k_sharded_step_fused(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
                                                                const double* mail, int mail_slot, double epoch, T* state, int options,
-                                                               unsigned long long timeout_ns, unsigned long long* wait_ns)
+                                                               unsigned long long timeout_ns, unsigned long long* wait_ns, int max_levels)
 {
     __shared__ int s_ok;
     if (level > 0 && state[5] != num<T>::zero()) {
@@ -905,7 +1114,7 @@ template <class T, int D> __global__ void k_sharded_step_fused(const T* low, con
         state[2] = res;
         state[3] = res;
         state[4] = err;
-        if (err <= fm::err_target(res, rtol, atol)) state[5] = num<T>::one();
+        if (err <= fm::err_target(res, rtol, atol) && may_stop(options, level, max_levels)) state[5] = num<T>::one();
     }
 }
 
@@ -914,7 +1123,7 @@ template <class T, int D> __global__ void k_sharded_step_fused(const T* low, con
 // state = {s_total.s, s_total.c, old_res, value, err, done, level_used, h}
 // state[5] (done): 0 running, 1 converged, 2 zero-width box under the quad() edge rules.
 template <class T, int D> __global__ void k_sharded_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
-                                                         const T* partials, T* state, int options)
+                                                         const T* partials, T* state, int options, int max_levels)
 {
     if (level > 0 && state[5] != num<T>::zero()) return;
     if (level == 0 && (options & OPT_QUAD_EDGE)) {  // any(low .== up) -> zero(T)   quad.jl:96-98,129-131
@@ -962,7 +1171,7 @@ template <class T, int D> __global__ void k_sharded_step(const T* low, const T* 
         state[2] = res;
         state[3] = res;
         state[4] = err;
-        if (err <= fm::err_target(res, rtol, atol)) state[5] = num<T>::one();
+        if (err <= fm::err_target(res, rtol, atol) && may_stop(options, level, max_levels)) state[5] = num<T>::one();
     }
 }
 

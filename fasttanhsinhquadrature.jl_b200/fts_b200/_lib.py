@@ -19,6 +19,7 @@ OK, ERR_INVALID_ARGUMENT, ERR_DIMENSION_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR
 F32, F64, DD64 = 0, 1, 2
 ORDER_REFERENCE, ORDER_FAST, ORDER_AUTO = 0, 1, 2
 OPT_QUAD_EDGE_RULES = 1
+OPT_FORCE_DEPTH = 2
 FLAG_CONVERGED, FLAG_MAX_LEVELS, FLAG_ZERO_WIDTH, FLAG_FLIPPED = 1, 2, 4, 8
 KIND_1D, KIND_2D, KIND_3D, KIND_1D_CMPL, KIND_2D_CMPL = 1, 2, 3, 4, 5
 
@@ -81,12 +82,16 @@ _SIGS = {
     "fts_integrand_nvrtc": (ci, [C.c_char_p, ci, ci, C.POINTER(vp), C.c_char_p, cs_]),
     "fts_integrand_info": (ci, [vp] + [C.POINTER(ci)] * 3),
     "fts_integrand_free": (ci, [vp]),
+    "fts_eval_batch": (ci, [vp, ci, vp, vp, ci, i64, vp]),
+    "fts_integrate1d_cmpl_batch": (ci, [vp, vp, ci, vp, ci, i64, vp]),
+    "fts_integrate1d_cmpl_batch_dev": (ci, [vp, vp, ci, vp, ci, i64, vp, vp]),
     "fts_integrate_batch": (ci, [vp, vp, ci, vp, vp, ci, vp, ci, i64, vp]),
     "fts_integrate_batch_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, ci, i64, vp, vp]),
     "fts_adaptive_batch": (ci, [vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, i64, vp, vp, vp, vp]),
     "fts_adaptive_batch_dev": (ci, [vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, i64, vp, vp, vp, vp, vp]),
     "fts_adaptive_sharded_level_dev": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]),
     "fts_adaptive_sharded_step_dev": (ci, [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp]),
+    "fts_adaptive_sharded_step_opts_dev": (ci, [vp, vp, vp, vp, vp, ci, ci, vp, vp, ci, ci, vp]),
     "fts_peer_mailbox_bytes": (ci, [ci, C.POINTER(cs_)]),
     "fts_peer_alloc": (ci, [cs_, C.POINTER(vp), vp]),
     "fts_peer_open": (ci, [vp, C.POINTER(vp)]),
@@ -94,6 +99,7 @@ _SIGS = {
     "fts_peer_free": (ci, [vp]),
     "fts_adaptive_sharded_fused_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp), C.c_uint64, vp, vp]),
     "fts_peer_wait_ns": (ci, [ci, C.POINTER(C.c_uint64)]),
+    "fts_adaptive_sharded_fused_opts_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp), C.c_uint64, vp, ci, vp]),
     "fts_integrand_cubin_size": (ci, [vp, C.POINTER(cs_), C.POINTER(ci)]),
     "fts_measure_fma_peak": (ci, [ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fts_launch_count": (i64, [ci]),

@@ -176,12 +176,12 @@ def sharded_level_dev(cache, f, *, low, up, params, level, rank, nranks, partial
                                                  C.c_void_p(stream) if stream else None))
 
 
-def sharded_step_dev(cache, *, low, up, rtol, atol, level, nranks, partials, state, stream=None) -> None:
-    """fts_adaptive_sharded_step_dev on device pointers (ints)."""
+def sharded_step_dev(cache, *, low, up, rtol, atol, level, nranks, partials, state, stream=None, options=0, max_levels=0) -> None:
+    """fts_adaptive_sharded_step_opts_dev on device pointers (ints)."""
     dt = cache.dtype
     r, a = _scalar(rtol, dt), _scalar(atol, dt)
-    L.check(L.lib.fts_adaptive_sharded_step_dev(cache.handle, C.c_void_p(low), C.c_void_p(up), _ptr(r), _ptr(a), level, nranks,
-                                                C.c_void_p(partials), C.c_void_p(state), C.c_void_p(stream) if stream else None))
+    L.check(L.lib.fts_adaptive_sharded_step_opts_dev(cache.handle, C.c_void_p(low), C.c_void_p(up), _ptr(r), _ptr(a), level, nranks,
+                                                     C.c_void_p(partials), C.c_void_p(state), options, max_levels, C.c_void_p(stream) if stream else None))
 
 
 # ------------------------------------------------------------------------------- integrands ---
@@ -243,6 +243,17 @@ def cuda_integrand(body: str, kind="1d", nparams: int = 0, name: str = "user") -
     if rc != L.OK:
         raise FtsError(rc, L.last_error() + "\n" + log.value.decode(errors="replace"))
     return Integrand(h, k, nparams, name, False)
+
+
+def evaluate(f: "Integrand", x, params=None, T=np.float64) -> np.ndarray:
+    """f(x) at the points x, evaluated on the device (fts_eval_batch; kind f(x), float32/float64)."""
+    dt = _dt(T)
+    xs = np.ascontiguousarray(np.asarray(x, dt).reshape(-1))
+    p, pstride, _ = _params(f, params, dt)
+    out = np.zeros(xs.shape[0], dt)
+    code = L.F32 if dt == np.dtype(np.float32) else L.F64
+    L.check(L.lib.fts_eval_batch(f._h, code, _ptr(xs), _ptr(p), pstride, xs.shape[0], _ptr(out)))
+    return out
 
 
 # ------------------------------------------------------------------------------- windows ------
@@ -426,6 +437,21 @@ def integrate1D(f, *args, params=None, order="reference"):
 def integrate1D_avx(f, *args, params=None):
     """integrate1D_avx   integrate1D.jl:124-157 (reassociated + FMA)"""
     return integrate1D(f, *args, params=params, order="fast")
+
+
+def integrate1D_cmpl(T, f, N: int, params=None, order="reference"):
+    """integrate1D_cmpl(T, f, N)   integrate1D.jl:49-65: integral of f(x, 1-x, 1+x) over [-1, 1] on the grid
+    tanhsinh(T, N), complements formed by subtraction (unexported in the reference as well)."""
+    if not isinstance(f, Integrand) or f.kind != L.KIND_1D_CMPL:
+        raise DimensionMismatch(L.ERR_DIMENSION_MISMATCH, "integrate1D_cmpl needs an integrand of kind f(x, bmx, xma)")
+    dt = _dt(T)
+    x, w, h = tanhsinh(dt, N)
+    handle = _tables.get(x, w, h)
+    p, pstride, npb = _params(f, params, dt)
+    batch = npb if npb else 1
+    out = np.zeros(batch, dt)
+    L.check(L.lib.fts_integrate1d_cmpl_batch(handle, f._h, _order(order), _ptr(p), pstride, batch, _ptr(out)))
+    return out if npb else out[0]
 
 
 def integrate2D(f, *args, params=None, order="reference"):
@@ -697,58 +723,62 @@ def _adaptive(name: str, T, f: Integrand, kind: int, low, up, *, rtol, atol, max
 _ADAPT_KW = dict(rtol=None, atol=0, warn=True, cache=None, params=None, full_output=False)
 
 
-def adaptive_integrate_1D(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, order="reference", full_output=False):
+# force_depth=True (additive, not in the reference): FTS_OPT_FORCE_DEPTH — every level up to max_levels is
+# computed whatever the error estimate says.  The reference's own forced-depth idiom, rtol = atol = 0
+# (benchmark/benchmarks.jl:95-110, runtests.jl:230), still stops when two levels agree to the last bit,
+# which smooth integrands do at depth 6-7.
+def adaptive_integrate_1D(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, order="reference", full_output=False, force_depth=False):
     """adaptive_integrate_1D(T, f, a, b; rtol, atol, max_levels=16, warn=true, cache)   adaptive.jl:28-85"""
     return _adaptive("adaptive_integrate_1D", T, f, L.KIND_1D, a, b, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn, cache=cache,
-                     params=params, order=order, full_output=full_output)
+                     params=params, order=order, full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_1D_avx(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, full_output=False):
+def adaptive_integrate_1D_avx(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, full_output=False, force_depth=False):
     """adaptive_integrate_1D_avx   adaptive.jl:94-143"""
     return _adaptive("adaptive_integrate_1D_avx", T, f, L.KIND_1D, a, b, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn, cache=cache,
-                     params=params, order="fast", full_output=full_output)
+                     params=params, order="fast", full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_1D_cmpl(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, order="reference", full_output=False):
+def adaptive_integrate_1D_cmpl(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, order="reference", full_output=False, force_depth=False):
     """adaptive_integrate_1D_cmpl   adaptive.jl:727-795; f(x, b-x, x-a)"""
     return _adaptive("adaptive_integrate_1D_cmpl", T, f, L.KIND_1D_CMPL, a, b, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn,
-                     cache=cache, params=params, order=order, full_output=full_output)
+                     cache=cache, params=params, order=order, full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_1D_cmpl_avx(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, full_output=False):
+def adaptive_integrate_1D_cmpl_avx(T, f, a, b, *, rtol=None, atol=0, max_levels=16, warn=True, cache=None, params=None, full_output=False, force_depth=False):
     """adaptive_integrate_1D_cmpl_avx   adaptive.jl:805-865"""
     return _adaptive("adaptive_integrate_1D_cmpl_avx", T, f, L.KIND_1D_CMPL, a, b, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn,
-                     cache=cache, params=params, order="fast", full_output=full_output)
+                     cache=cache, params=params, order="fast", full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_2D(T, f, low, up, *, rtol=None, atol=0, max_levels=8, warn=True, cache=None, params=None, order="reference", full_output=False):
+def adaptive_integrate_2D(T, f, low, up, *, rtol=None, atol=0, max_levels=8, warn=True, cache=None, params=None, order="reference", full_output=False, force_depth=False):
     """adaptive_integrate_2D   adaptive.jl:154-233"""
     return _adaptive("adaptive_integrate_2D", T, f, L.KIND_2D, low, up, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn, cache=cache,
-                     params=params, order=order, full_output=full_output)
+                     params=params, order=order, full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_2D_avx(T, f, low, up, *, rtol=None, atol=0, max_levels=8, warn=True, cache=None, params=None, full_output=False):
+def adaptive_integrate_2D_avx(T, f, low, up, *, rtol=None, atol=0, max_levels=8, warn=True, cache=None, params=None, full_output=False, force_depth=False):
     """adaptive_integrate_2D_avx   adaptive.jl:242-342"""
     return _adaptive("adaptive_integrate_2D_avx", T, f, L.KIND_2D, low, up, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn, cache=cache,
-                     params=params, order="fast", full_output=full_output)
+                     params=params, order="fast", full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_2D_cmpl(T, f, low, up, *, rtol=None, atol=0, max_levels=8, warn=True, cache=None, params=None, order="reference", full_output=False):
+def adaptive_integrate_2D_cmpl(T, f, low, up, *, rtol=None, atol=0, max_levels=8, warn=True, cache=None, params=None, order="reference", full_output=False, force_depth=False):
     """Tensor-complement adaptive 2D (extension, BASELINE config C): f(x, y, b-x, x-a, d-y, y-c)."""
     return _adaptive("adaptive_integrate_2D_cmpl", T, f, L.KIND_2D_CMPL, low, up, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn,
-                     cache=cache, params=params, order=order, full_output=full_output)
+                     cache=cache, params=params, order=order, full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_3D(T, f, low, up, *, rtol=None, atol=0, max_levels=5, warn=True, cache=None, params=None, order="reference", full_output=False):
+def adaptive_integrate_3D(T, f, low, up, *, rtol=None, atol=0, max_levels=5, warn=True, cache=None, params=None, order="reference", full_output=False, force_depth=False):
     """adaptive_integrate_3D   adaptive.jl:352-480"""
     return _adaptive("adaptive_integrate_3D", T, f, L.KIND_3D, low, up, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn, cache=cache,
-                     params=params, order=order, full_output=full_output)
+                     params=params, order=order, full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
-def adaptive_integrate_3D_avx(T, f, low, up, *, rtol=None, atol=0, max_levels=5, warn=True, cache=None, params=None, full_output=False):
+def adaptive_integrate_3D_avx(T, f, low, up, *, rtol=None, atol=0, max_levels=5, warn=True, cache=None, params=None, full_output=False, force_depth=False):
     """adaptive_integrate_3D_avx   adaptive.jl:489-715"""
     return _adaptive("adaptive_integrate_3D_avx", T, f, L.KIND_3D, low, up, rtol=rtol, atol=atol, max_levels=max_levels, warn=warn, cache=cache,
-                     params=params, order="fast", full_output=full_output)
+                     params=params, order="fast", full_output=full_output, options=L.OPT_FORCE_DEPTH if force_depth else 0)
 
 
 # ------------------------------------------------------------------------------- quad ---------

@@ -159,7 +159,8 @@ class ShardedPlan:
     synchronises and reads the 8-element state."""
 
     def __init__(self, T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
-                 shard_from_level: Optional[int] = None, exchange: str = "peer", world: Optional[int] = None, rank: Optional[int] = None):
+                 shard_from_level: Optional[int] = None, exchange: str = "peer", world: Optional[int] = None, rank: Optional[int] = None,
+                 force_depth: bool = False):
         import torch
         dist = _dist()
         self.dt = dt = api._dt(T)
@@ -170,6 +171,7 @@ class ShardedPlan:
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.group, self.f, self.exchange, self.max_levels = group, f, exchange, max_levels
+        self.options = L.OPT_FORCE_DEPTH if force_depth else 0
         self.rtol_T, self.atol_T = api._resolve_tolerances(dt, rtol, atol)
         self.dim = f.dim
         if cache is None:
@@ -204,10 +206,10 @@ class ShardedPlan:
             if mb is not None:
                 mb.epoch += 1
                 epoch = mb.epoch
-            L.check(L.lib.fts_adaptive_sharded_fused_dev(
+            L.check(L.lib.fts_adaptive_sharded_fused_opts_dev(
                 cache.handle, f._h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(p.data_ptr()) if p is not None else None,
                 api._ptr(self.rtol_T), api._ptr(self.atol_T), self.max_levels, self.shard_from_level, self.rank, self.world,
-                mb.ptrs if mb is not None else None, C.c_uint64(epoch), C.c_void_p(state.data_ptr()), C.c_void_p(stream)))
+                mb.ptrs if mb is not None else None, C.c_uint64(epoch), C.c_void_p(state.data_ptr()), self.options, C.c_void_p(stream)))
             return
         dist = _dist()
         partial, gathered, world, group = self.partial, self.gathered, self.world, self.group
@@ -226,7 +228,7 @@ class ShardedPlan:
 
         def step_fn(level, parts):
             api.sharded_step_dev(cache, low=lo.data_ptr(), up=hi.data_ptr(), rtol=self.rtol_T[0], atol=self.atol_T[0], level=level, nranks=parts.shape[0],
-                                 partials=parts.data_ptr(), state=state.data_ptr(), stream=stream)
+                                 partials=parts.data_ptr(), state=state.data_ptr(), stream=stream, options=self.options, max_levels=self.max_levels)
 
         run_sharded_levels(self.max_levels, self.rank, world, level_fn, step_fn, all_gather, self.shard_from_level)
 
@@ -245,7 +247,7 @@ class ShardedPlan:
 
 
 def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
-                               warn: bool = True, shard_from_level: Optional[int] = None, exchange: str = "peer"):
+                               warn: bool = True, shard_from_level: Optional[int] = None, exchange: str = "peer", force_depth: bool = False):
     """One large adaptive 2D/3D integral over all ranks of `group`.  Returns an AdaptiveResult
     with one element, identical on every rank.
 
@@ -253,7 +255,7 @@ def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: 
     mailbox over NVLink peer memory, the stop test waits on the device; ONE C call queues all
     levels.  exchange="nccl": level kernel -> NCCL all-gather -> stop-test kernel per level."""
     plan = ShardedPlan(T, f, low, up, rtol=rtol, atol=atol, max_levels=max_levels, cache=cache, params=params, group=group,
-                       shard_from_level=shard_from_level, exchange=exchange)
+                       shard_from_level=shard_from_level, exchange=exchange, force_depth=force_depth)
     plan.launch()
     s = plan.result()
     dt, dim, rank = plan.dt, plan.dim, plan.rank

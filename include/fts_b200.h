@@ -14,7 +14,8 @@
  *  - scalar arguments of the working precision are passed as `const void*` pointing at ONE
  *    element of the dtype (float / double / fts_dd), arrays as `const void*` to `count` elements.
  *  - `*_batch` entry points take HOST buffers (caller-owned, only read/written during the call)
- *    and move them over PCIe themselves; `*_batch_dev` take DEVICE pointers on `stream`
+ *    and move them over PCIe themselves; they are re-entrant — every host thread gets its own
+ *    stream and device scratch, two threads run two calls side by side; `*_batch_dev` take DEVICE pointers on `stream`
  *    (a cudaStream_t passed as void*, NULL = legacy default stream) and are asynchronous.
  *  - layout: bounds `low`,`up` are [batch][D] row-major (a Julia Vector{SVector{D,T}});
  *    `bounds_stride` = D for per-integral boxes or 0 to broadcast one box to the whole batch.
@@ -73,7 +74,11 @@ enum {
     /* quad()/quad_cmpl() edge rules (quad.jl:41-46, 96-115, 129-153, 303-308):
        any low==up -> exactly 0; flipped bounds -> swap and negate. Without this bit the typed
        adaptive_integrate_* semantics apply (bounds used as given). */
-    FTS_OPT_QUAD_EDGE_RULES = 1
+    FTS_OPT_QUAD_EDGE_RULES = 1,
+    /* Forced depth (additive; not in the reference): the stop rule is only applied at level ==
+       max_levels, so every level is computed.  The reference's forced-depth idiom rtol = atol = 0
+       (benchmark/benchmarks.jl:95-110) still stops as soon as two levels agree to the last bit. */
+    FTS_OPT_FORCE_DEPTH = 2
 };
 
 /* ---- per-integral result flags ----------------------------------------------------------- */
@@ -238,6 +243,14 @@ int fts_integrand_info(fts_integrand f, int* kind, int* nparams, int* is_builtin
 int fts_integrand_cubin_size(fts_integrand f, size_t* bytes, int* nkernels);
 int fts_integrand_free(fts_integrand f);
 
+/* Pointwise values out[b] = f(x[b], params[b]) of an integrand of kind FTS_KIND_1D, evaluated on the
+ * device with the arithmetic of the FAST kernels (HOST buffers, synchronous; f32/f64).  Not in the
+ * reference (there f is a Julia callable one can simply call): it lets a caller check an NVRTC body
+ * or a builtin family — the tests hold the table-driven exp/log of the builtin families to their ulp
+ * bounds with it. */
+int fts_eval_batch(fts_integrand f, int dtype, const void* x, const void* params, int params_stride,
+                   int64_t n, void* out_value);
+
 /* ---- launches: fixed grids ----------------------------------------------------------------- */
 /* integrate{1,2,3}D(f, low, up, x, w, h) / integrate{1,2,3}D_avx
  * (integrate1D.jl:90-102,138-147; integrate2D.jl:91-124,46-73; integrate3D.jl:150-207,68-123).
@@ -251,6 +264,16 @@ int fts_integrate_batch_dev(fts_tables t, fts_integrand f, int order,
                             const void* low, const void* up, int bounds_stride,
                             const void* params, int params_stride,
                             int64_t batch, void* out_value, void* stream);
+
+/* integrate1D_cmpl(T, f, N) (integrate1D.jl:49-65; unexported in the reference, tested at
+ * test/families_1d.jl:20): integral over [-1, 1] of f(x, 1-x, 1+x) on the fixed grid `t`, the
+ * complements formed by subtraction as the reference does.  One integral per parameter row
+ * (`batch` rows; a family without parameters gives `batch` copies).  f must be of kind
+ * FTS_KIND_1D_CMPL.  f32/f64. */
+int fts_integrate1d_cmpl_batch(fts_tables t, fts_integrand f, int order, const void* params,
+                               int params_stride, int64_t batch, void* out_value);
+int fts_integrate1d_cmpl_batch_dev(fts_tables t, fts_integrand f, int order, const void* params,
+                                   int params_stride, int64_t batch, void* out_value, void* stream);
 
 /* ---- launches: adaptive -------------------------------------------------------------------- */
 /* adaptive_integrate_{1D,2D,3D,1D_cmpl}[_avx] (adaptive.jl:28-75, 94-133, 154-224, 242-333,
@@ -293,6 +316,11 @@ int fts_adaptive_sharded_level_dev(fts_cache c, fts_integrand f,
 int fts_adaptive_sharded_step_dev(fts_cache c, const void* low, const void* up,
                                   const void* rtol, const void* atol, int level, int nranks,
                                   const void* partials_dev, void* state_dev, void* stream);
+/* the same with launch option bits; max_levels tells FTS_OPT_FORCE_DEPTH which level is the last */
+int fts_adaptive_sharded_step_opts_dev(fts_cache c, const void* low, const void* up,
+                                       const void* rtol, const void* atol, int level, int nranks,
+                                       const void* partials_dev, void* state_dev, int options,
+                                       int max_levels, void* stream);
 
 /* Fused variant ("one kernel does the compute and the exchange"): ONE call queues every level of
  * the integral.  The epilogue of each level kernel stores this rank's (s, c) and then an epoch
@@ -313,6 +341,12 @@ int fts_adaptive_sharded_fused_dev(fts_cache c, fts_integrand f, const void* low
                                    int max_levels, int shard_from_level, int rank, int nranks,
                                    void* const* mailboxes, uint64_t epoch, void* state_dev,
                                    void* stream);
+/* the same with launch option bits (FTS_OPT_QUAD_EDGE_RULES, FTS_OPT_FORCE_DEPTH) */
+int fts_adaptive_sharded_fused_opts_dev(fts_cache c, fts_integrand f, const void* low, const void* up,
+                                        const void* params, const void* rtol, const void* atol,
+                                        int max_levels, int shard_from_level, int rank, int nranks,
+                                        void* const* mailboxes, uint64_t epoch, void* state_dev,
+                                        int options, void* stream);
 
 /* Per-level exchange wait of the LAST fts_adaptive_sharded_fused_dev call of this process: out[l] =
  * nanoseconds (%globaltimer) the device-side stop test of level l spent spinning on the slowest

@@ -112,6 +112,9 @@ class Oracle:
             f = getattr(L, f"fts_or_integrate1d_{sfx}")
             f.restype = ct
             f.argtypes = [C.c_int, vp, vp, ct, ct, vp, vp, C.c_int, ct]
+            f = getattr(L, f"fts_or_integrate1d_cmpl_{sfx}")
+            f.restype = ct
+            f.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, ct]
             for d in ("2d", "3d"):
                 f = getattr(L, f"fts_or_integrate{d}_{sfx}")
                 f.restype = ct
@@ -230,6 +233,11 @@ class Oracle:
         ct = _c_t(dtype); pa = self._p(dtype, p)
         return getattr(self.lib, f"fts_or_integrate1d_{dtype}")(
             fam, _ptr(pa), cb, ct(low), ct(up), _ptr(x), _ptr(w), len(x), ct(h))
+
+    def integrate1d_cmpl(self, dtype, fam, p, x, w, h, cb=None):
+        """integrate1D_cmpl(T, f, N) on the grid (x, w, h) = tanhsinh(T, N)   src/integrate1D.jl:49-65"""
+        ct = _c_t(dtype); pa = self._p(dtype, p)
+        return getattr(self.lib, f"fts_or_integrate1d_cmpl_{dtype}")(fam, _ptr(pa), cb, _ptr(x), _ptr(w), len(x), ct(h))
 
     def integrate_nd(self, dtype, D, fam, p, low, up, x, w, h, cb=None):
         """integrate2D / integrate3D   src/integrate2D.jl:91-124, src/integrate3D.jl:150-207"""

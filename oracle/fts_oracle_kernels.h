@@ -28,6 +28,29 @@ T K(fts_or_integrate1d)(int fam, const T* p, void* cb, T low, T up, const T* x, 
 #endif
 }
 
+/* src/integrate1D.jl:49-65 integrate1D_cmpl(T, f, N): f(x, 1-x, 1+x) over [-1,1] on the grid
+ * (x, w, h) = tanhsinh(T, N); the complements are formed by subtraction */
+T K(fts_or_integrate1d_cmpl)(int fam, const T* p, void* cb, const T* x, const T* w, int n, T h)
+{
+    S(fts_or_fn) f = {fam, p, cb};
+    T one = (T)1;
+    ACC s = (ACC)(S(half_pi)() * S(FC1)(&f, (T)0, one, one));
+    for (int i = 0; i < n; ++i) {
+        T xi = x[i];
+        T one_minus_x = one - xi, one_plus_x = one + xi;
+#if ACC_IS_T
+        s += w[i] * (S(FC1)(&f, xi, one_minus_x, one_plus_x) + S(FC1)(&f, -xi, one_plus_x, one_minus_x));
+#else
+        s += (ACC)w[i] * ((ACC)S(FC1)(&f, xi, one_minus_x, one_plus_x) + (ACC)S(FC1)(&f, -xi, one_plus_x, one_minus_x));
+#endif
+    }
+#if ACC_IS_T
+    return h * s;
+#else
+    return (T)((ACC)h * s);
+#endif
+}
+
 /* src/integrate2D.jl:91-124 */
 T K(fts_or_integrate2d)(int fam, const T* p, void* cb, const T* low, const T* up, const T* x,
                         const T* w, int n, T h)

@@ -774,6 +774,95 @@ def test_on_device_table_generation(gpu):
     assert abs(gpu.dd_to_mpf(vd)[0] - (mpmath.exp(-1) - mpmath.e1(1))) < mpmath.mpf("1e-28")
 
 
+def test_integrate1d_cmpl_fixed_grid(gpu, oracle):
+    """integrate1D_cmpl(T, f, N) (integrate1D.jl:49-65, KAT test/families_1d.jl:20): reference order bit-level
+    against the oracle, the FMA order against the exactly-summed oracle, a batch of parameter rows, Float32."""
+    x, w, h = gpu.tanhsinh(np.float64, 120)
+    f = gpu.builtin("c_invsqrt")
+    v = gpu.integrate1D_cmpl(np.float64, f, 120, params=[1.0])
+    assert abs(v - PI) < 5e-8                                                                 # families_1d.jl:20
+    assert rel(v, oracle.integrate1d_cmpl("f64", F["C1_INVSQRT"], [1.0], x, w, h)) <= 4e-16
+    vf = gpu.integrate1D_cmpl(np.float64, f, 120, params=[1.0], order="fast")
+    assert rel(vf, oracle.integrate1d_cmpl("f64x", F["C1_INVSQRT"], [1.0], x, w, h)) <= 1e-14
+    cs = np.linspace(0.5, 2.0, 257).reshape(-1, 1)
+    vb = gpu.integrate1D_cmpl(np.float64, f, 120, params=cs)
+    assert vb.shape == (257,) and rel(vb, cs[:, 0] * v).max() <= 4e-15
+    for name, fam in (("c_log_bmx", F["C1_LOG_BMX"]), ("c_exp_plus", F["C1_EXP_PLUS"]), ("c_exp_inv_bmx", F["C1_EXP_INV_BMX"])):
+        got = gpu.integrate1D_cmpl(np.float64, gpu.builtin(name), 80)
+        xx, ww, hh = gpu.tanhsinh(np.float64, 80)
+        assert rel(got, oracle.integrate1d_cmpl("f64", fam, None, xx, ww, hh)) <= RTOL64, name
+    v32 = gpu.integrate1D_cmpl(np.float32, gpu.builtin("c_exp_plus"), 60)
+    assert v32.dtype == np.float32 and abs(v32 - (math.e - 1 / math.e + 4)) < 1e-4
+    with pytest.raises(gpu.DimensionMismatch):
+        gpu.integrate1D_cmpl(np.float64, gpu.builtin("exp"), 80)
+
+
+def test_host_entry_points_are_reentrant(gpu):
+    """Two host threads drive two streams at once (every thread owns its stream and device scratch): the
+    host-buffer calls of both threads — pinned in-place buffers and pageable staged ones — return what the
+    same calls return one after the other, bit for bit."""
+    import threading
+    from fts_b200 import _lib as L
+    cache = gpu.adaptive_cache_1D(np.float64, max_levels=16)
+    f = gpu.builtin("gauss")
+    n = 200_000
+    alphas = [0.5 + 49.5 * np.arange(n) / (n - 1), 1.0 + 30.0 * np.random.default_rng(3).random(n)]
+    x, w, h = gpu.tanhsinh(np.float64, 80)
+
+    def work(k, alloc, out, reps):
+        al = alloc(n); al[...] = alphas[k]
+        lo, hi = alloc(1), alloc(1); lo[...] = -1.0; hi[...] = 1.0
+        v, lv = alloc(n), alloc(n, np.int32)
+        res = []
+        for _ in range(reps):
+            gpu.adaptive_batch_host(cache, f, low=lo.ctypes.data, up=hi.ctypes.data, bounds_stride=0, params=al.ctypes.data, params_stride=1,
+                                    rtol=1e-10, atol=0.0, max_levels=16, batch=n, value=v.ctypes.data, levels=lv.ctypes.data, order="reference",
+                                    options=L.OPT_QUAD_EDGE_RULES)
+            res.append((v.copy(), lv.copy()))
+            fx = gpu.integrate1D(gpu.builtin("exp"), np.zeros(1000), 1.0 + alphas[k][:1000] / 50, x, w, h)   # a second entry point in between
+            res.append((fx.copy(), None))
+        out[k] = res
+
+    pageable = lambda shape, dt=np.float64: np.empty(shape, dt)
+    for alloc in (gpu.pinned_empty, pageable):
+        serial, parallel = {}, {}
+        for k in (0, 1):
+            work(k, alloc, serial, 1)
+        threads = [threading.Thread(target=work, args=(k, alloc, parallel, 6)) for k in (0, 1)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for k in (0, 1):
+            assert len(parallel[k]) == 12
+            for i, (val, lev) in enumerate(parallel[k]):
+                want = serial[k][i % 2]
+                assert np.array_equal(val, want[0]) and (lev is None or np.array_equal(lev, want[1])), (k, i)
+
+
+def test_optimal_spacing_grids_through_the_fixed_grid_kernels(gpu, oracle):
+    """tanhsinh_opt grids (core.jl:276-302; a node count that differs from N div 2 and a spacing
+    h = hopt != tmax/n) fed through integrate{1,2,3}D in both orders: against the oracle on the same nodes,
+    and against the closed forms."""
+    for N in (40, 81):
+        x, w, h = gpu.tanhsinh_opt(np.float64, N)
+        assert len(x) != N // 2 or abs(h - float(gpu.tmax(np.float64)) / (N // 2)) > 1e-6
+        e1 = math.e - 1 / math.e
+        for order, sfx in (("reference", "f64"), ("fast", "f64x")):
+            v1 = gpu.integrate1D(gpu.builtin("exp"), -1.0, 1.0, x, w, h, order=order)
+            assert rel(v1, oracle.integrate1d(sfx, F["F1_EXP"], None, -1.0, 1.0, x, w, h)) <= RTOL64 and abs(v1 - e1) < 1e-13
+            lo2, up2 = [-1.0, 0.0], [1.0, 2.0]
+            v2 = gpu.integrate2D(gpu.builtin("exp_2d"), lo2, up2, x, w, h, order=order)
+            assert rel(v2, oracle.integrate_nd(sfx, 2, F["F2_EXP"], None, lo2, up2, x, w, h)) <= RTOL64 and rel(v2, e1 * (math.e ** 2 - 1)) < 1e-13
+            lo3, up3 = [-2.0, -1.0, 0.0], [3.0, 2.0, 4.0]
+            v3 = gpu.integrate3D(gpu.builtin("exp_3d"), lo3, up3, x, w, h, order=order)
+            assert rel(v3, oracle.integrate_nd(sfx, 3, F["F3_EXP"], None, lo3, up3, x, w, h)) <= RTOL64
+            assert rel(v3, np.prod(np.exp(up3) - np.exp(lo3))) < 1e-12
+    x32, w32, h32 = gpu.tanhsinh_opt(np.float32, 30)
+    v32 = gpu.integrate1D(gpu.builtin("poly6"), x32, w32, h32)
+    assert v32.dtype == np.float32 and abs(v32 - 9 / 7) < 2e-5
+
+
 # ------------------------------------------------------------------ BASELINE sizes: D and E ---
 @pytest.mark.parametrize("box", ["unit", "aniso"])
 def test_config_d_deep_levels_against_oracle(gpu, oracle, box):
@@ -789,15 +878,17 @@ def test_config_d_deep_levels_against_oracle(gpu, oracle, box):
     for L in (7, 8):
         refx = oracle.adaptive3d_omp_f64x(F["F3_EXP"], None, lo, up, 0.0, 0.0, L, oc)
         assert refx.level == L and refx.evals == (2 * (2 << L) + 1) ** 3
-        r = gpu.adaptive_integrate_3D_avx(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, warn=False, cache=cache, full_output=True)
+        # force_depth: with rtol = atol = 0 alone the compensated GPU sums of exp(x+y+z) agree to the last bit at
+        # levels 6 and 7 and the reference's stop rule (err <= 0) ends the integral there
+        r = gpu.adaptive_integrate_3D_avx(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, warn=False, cache=cache, full_output=True, force_depth=True)
         assert r.levels[0] == L and int(gpu.evals_for_level(3, r.levels)[0]) == refx.evals
         assert rel(r.value[0], refx.value) <= RTOL64, (box, L, r.value[0], refx.value)
-        assert rel(r.err[0], refx.err) <= 1e-3 or abs(r.err[0] - refx.err) <= 1e-14 * abs(refx.value)
+        assert abs(r.err[0] - refx.err) <= 1e-14 * abs(refx.value)
         assert rel(r.value[0], exact) <= 1e-12
         # the multi-GPU entry point on one rank (fused exchange path and the all-gather path) gives the same integral
         from fts_b200 import distributed as fd
         for exchange in ("peer", "nccl"):
-            rs = fd.adaptive_integrate_sharded(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, cache=cache, exchange=exchange, warn=False)
+            rs = fd.adaptive_integrate_sharded(np.float64, f, lo, up, rtol=0.0, atol=0.0, max_levels=L, cache=cache, exchange=exchange, warn=False, force_depth=True)
             assert rs.levels[0] == L and rel(rs.value[0], refx.value) <= RTOL64, (box, L, exchange)
     # tolerance mode (rtol = 1e-9): same stop level as the oracle
     refx = oracle.adaptive3d_omp_f64x(F["F3_EXP"], None, lo, up, 1e-9, 0.0, 8, oc)

@@ -296,3 +296,17 @@ def test_turbo_twin_against_scalar_oracle(oracle):
         v = tw.batch_integrate1d(F["F1_EXP"], None, np.zeros(33), ups, x, w, h)
         vs = np.array([oracle.integrate1d("f64", F["F1_EXP"], None, 0.0, u, x, w, h) for u in ups])
         assert np.max(np.abs(v - vs) / vs) < 1e-14 and np.max(np.abs(v - (np.exp(ups) - 1))) < 1e-13
+
+
+def test_integrate1d_cmpl_kat(oracle):
+    """integrate1D_cmpl(Float64, cmpl_sing, 120) ~ pi to 5e-8 (test/families_1d.jl:20): the fixed-grid complement
+    entry forms 1 -+ x by subtraction, so it is NOT complement-accurate — the loose tolerance
+    is the reference's own."""
+    x, w, h = oracle.tanhsinh("f64", 120)
+    v = oracle.integrate1d_cmpl("f64", F["C1_INVSQRT"], [1.0], x, w, h)
+    assert abs(v - PI) < 5e-8
+    vx = oracle.integrate1d_cmpl("f64x", F["C1_INVSQRT"], [1.0], x, w, h)
+    assert abs(vx - v) < 1e-13
+    x32, w32, h32 = oracle.tanhsinh("f32", 60)
+    v32 = oracle.integrate1d_cmpl("f32", F["C1_EXP_PLUS"], None, x32, w32, h32)     # exp(x) + (1-x) + (1+x): e - 1/e + 4
+    assert abs(v32 - (math.e - 1 / math.e + 4)) < 1e-4

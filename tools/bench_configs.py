@@ -201,9 +201,15 @@ def case_dk(reps):
     partial = torch.zeros(2, dtype=torch.float64, device=dev)
     cache = fts.adaptive_cache_3D(np.float64, max_levels=8)
     stream = torch.cuda.current_stream().cuda_stream
-    for name, flop in (("exp_3d", 32.1), ("x2y2z2", 6.0), ("log_3d", None)):
+    only = os.environ.get("FTS_BENCH_DK")  # e.g. "log_3d:8": one family / level (for an ncu capture)
+    fams = (("exp_3d", 32.1), ("x2y2z2", 6.0), ("log_3d", 35.0), ("invsqrt_3d", 14.5), ("rat_3d", 12.0))  # nominal flop/eval (exp 29, log 35, rsqrt 12)
+    for name, flop in fams:
+        if only and name != only.split(":")[0]:
+            continue
         f = fts.builtin(name)
         for level in (6, 7, 8):
+            if only and level != int(only.split(":")[1]):
+                continue
             n = 2 << level
             evals = 7 * n ** 3 + 9 * n ** 2 + 3 * n
             ts = []
