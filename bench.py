@@ -457,7 +457,8 @@ def main():
         p_steps = max(5, args.steps // 4)
         p_ms, p_dev, _ = timed_region(step_o, p_steps)
         permuted = {"order": "sorted sweep" if PERMUTE else "permuted, seed 0", "steps": p_steps, "ms_per_step": p_dev / p_steps,
-                    "value": total_integrals / (p_dev / p_steps * 1e-3), "step_ms_min": min(p_ms)}
+                    "value": total_integrals / (p_dev / p_steps * 1e-3), "step_ms_min": min(p_ms), "step_ms_median": float(np.median(p_ms)),
+                    "step_ms_max": max(p_ms)}
 
     # ---- timed region 2: end to end through the host-buffer C ABI call (pinned host memory)
     h_alpha = torch.from_numpy(alpha_np).pin_memory()

@@ -734,6 +734,24 @@ static int launch_raw(const void* fn, unsigned grid, int block, size_t smem, voi
 // programmatic stream serialisation, so its CTAs are set up while the first kernel's last wave still runs
 // and wait in `griddepcontrol.wait` for the first kernel's completion and memory flush — the launch
 // latency of the second kernel (4-8 us on an idle stream) disappears behind the first.
+static int launch_dependent_params(const void* fn, unsigned grid, int block, void** params, cudaStream_t s)
+{
+    static const bool use_pdl = [] { const char* e = getenv("FTS_B200_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    FTS_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
+    g_launches.fetch_add(1);
+    return FTS_OK;
+}
+
 static int launch_dependent(const void* fn, unsigned grid, int block, size_t smem, void* args, cudaStream_t s)
 {
     static const bool use_pdl = [] { const char* e = getenv("FTS_B200_PDL"); return !e || atoi(e) != 0; }();
@@ -1127,13 +1145,20 @@ static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int o
     return FTS_OK;
 }
 
-// Persistent per-stream queue of the deep-level hand-off: {count, ticket, idx[capacity]}.  Launches
-// on one stream are ordered, so they can share a queue (the tail kernel re-arms it when it leaves);
-// different streams get different queues.
-struct TailQueue { int* buf = nullptr; size_t cap = 0; };
+// Persistent per-stream queues of the deep-level hand-off and of the bucket passes:
+// {count, ticket, sort_ctl[2], pad[4], idx[capacity], bucket arrays[2 * capacity + capacity / 16] (see Args::sort_idx)}.  Launches on one stream are
+// ordered, so they can share the queues (the tail kernel re-arms them when it leaves); different streams
+// get different ones.
+constexpr int QUEUE_HEADER = 8;
+struct TailQueue {
+    int* buf = nullptr;
+    size_t cap = 0;
+    int* fb_host = nullptr;  // pinned, device-mapped word: did the last call on this stream see incoherent warps? (see run_adaptive)
+    int* fb_dev = nullptr;
+};
 static std::mutex g_tail_mu;
 static std::vector<std::pair<cudaStream_t, TailQueue>> g_tail_queues;
-static int tail_queue_for(cudaStream_t s, size_t batch, int** out)
+static int tail_queue_for(cudaStream_t s, size_t batch, int** out, size_t* cap_out = nullptr, TailQueue* q_out = nullptr)
 {
     std::lock_guard<std::mutex> lk(g_tail_mu);
     TailQueue* q = nullptr;
@@ -1150,12 +1175,19 @@ static int tail_queue_for(cudaStream_t s, size_t batch, int** out)
             q->buf = nullptr;
             q->cap = 0;
         }
-        const size_t cap = batch + batch / 4 + 1024;
-        FTS_CUDA(cudaMalloc((void**)&q->buf, sizeof(int) * (cap + 2)));
-        FTS_CUDA(cudaMemsetAsync(q->buf, 0, sizeof(int) * 2, s));  // ordered before the first kernel on `s` (non-blocking streams do not wait for the legacy stream)
+        const size_t cap = (batch + batch / 4 + 2 * 1024) / 1024 * 1024;
+        FTS_CUDA(cudaMalloc((void**)&q->buf, sizeof(int) * (3 * cap + cap / 16 + QUEUE_HEADER)));
+        FTS_CUDA(cudaMemsetAsync(q->buf, 0, sizeof(int) * QUEUE_HEADER, s));  // ordered before the first kernel on `s` (non-blocking streams do not wait for the legacy stream)
         q->cap = cap;
     }
+    if (!q->fb_host) {
+        FTS_CUDA(cudaHostAlloc((void**)&q->fb_host, sizeof(int), cudaHostAllocMapped));
+        *q->fb_host = 0;
+        FTS_CUDA(cudaHostGetDevicePointer((void**)&q->fb_dev, q->fb_host, 0));
+    }
     *out = q->buf;
+    if (cap_out) *cap_out = q->cap;
+    if (q_out) *q_out = *q;  // a copy: the vector may grow under another thread once the lock is gone
     return FTS_OK;
 }
 
@@ -1165,8 +1197,10 @@ static void drop_device_state()
 {
     {
         std::lock_guard<std::mutex> lk(g_tail_mu);
-        for (auto& e : g_tail_queues)
+        for (auto& e : g_tail_queues) {
             if (e.second.buf) cudaFree(e.second.buf);
+            if (e.second.fb_host) cudaFreeHost(e.second.fb_host);
+        }
         g_tail_queues.clear();
     }
     if (g_peer_wait) cudaFree(g_peer_wait);
@@ -1237,7 +1271,7 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
             if (int rc = tail_queue_for(s, (size_t)batch, &queue)) return rc;
             a.tail_count = queue;
             a.ticket = (unsigned int*)(queue + 1);
-            a.tail_idx = queue + 2;
+            a.tail_idx = queue + QUEUE_HEADER;
             a.group = 32;
             a.level = lw;
             if (int rc = launch_raw(fn_warp, (unsigned)((batch + warps - 1) / warps), warps * 32, smem_w, &a, s)) return rc;
@@ -1277,16 +1311,54 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     const int tail_level = is_dd ? 7 : 8;
     const void* fn_tail = (dim == 1 && max_levels > tail_level) ? integrand_kernel(f, c->dtype, KID_ADAPT_TAIL, fast) : nullptr;
     a.tail_level = -1;
+    const void* fn_bucket = nullptr;
     if (fn_tail) {
         if (batch > 0x7fffffffLL) return set_error(FTS_ERR_INVALID_ARGUMENT, "batch too large for one launch");
         int* queue = nullptr;
-        if (int rc = tail_queue_for(s, (size_t)batch, &queue)) return rc;
+        size_t qcap = 0;
+        TailQueue tq;
+        if (int rc = tail_queue_for(s, (size_t)batch, &queue, &qcap, &tq)) return rc;
         a.tail_level = tail_level;
         a.tail_count = queue;
         a.ticket = (unsigned int*)(queue + 1);
-        a.tail_idx = queue + 2;
+        a.sort_ctl = queue + 2;
+        a.tail_idx = queue + QUEUE_HEADER;
+        // Bucket passes (Float64 exp families, big batches): warps whose lanes hold unrelated integrals leave them to
+        // k_bucket_sort + k_adaptive1d_bucket, which regroup them.  Two launches that a batch in coherent order does not
+        // need (5 us of a 280 us call when they find nothing to do), so they are armed by feedback: every call detects
+        // incoherent warps (k_adaptive1d_tpi) and the tail kernel leaves the finding in a pinned word; a call arms the
+        // passes when the last finished call on its stream found such warps.  Results do not depend on the choice, bit
+        // for bit.  FTS_B200_BUCKET = 0: never armed, 2: always armed, 1 (default): by feedback.
+        static const int bucket_mode = [] { const char* e = getenv("FTS_B200_BUCKET"); return e ? atoi(e) : 1; }();
+        if (bucket_mode != 0 && !cmpl && c->dtype == FTS_F64 && batch >= 4LL * g_prop.multiProcessorCount * 256) {
+            fn_bucket = integrand_kernel(f, c->dtype, KID_ADAPT_BUCKET, fast);
+            if (!fn_bucket) g_last_error.clear();
+            else {
+                // the two kernels are loaded (lazy module loading: ~0.4 ms) while the passes are not armed yet, not
+                // in the first call that needs them
+                static std::atomic<const void*> loaded{nullptr};
+                if (loaded.load() != fn_bucket) {
+                    cudaFuncAttributes fa;
+                    cudaFuncGetAttributes(&fa, (const void*)&fts::k_bucket_sort<void>);
+                    cudaFuncGetAttributes(&fa, fn_bucket);
+                    cudaGetLastError();
+                    loaded.store(fn_bucket);
+                }
+                a.sort_fb = tq.fb_dev;
+                if (bucket_mode == 2 || *(volatile int*)tq.fb_host != 0) a.sort_idx = queue + QUEUE_HEADER + qcap;
+                else fn_bucket = nullptr;  // detect only
+            }
+        }
     }
     if (int rc = launch(fn, batch, tpi_block(dim, c->dtype), &a, s)) return rc;
+    if (fn_bucket) {
+        const int* ctl = a.sort_ctl;
+        int* base = a.sort_idx;
+        long long nb = batch;
+        void* params[] = {(void*)&ctl, (void*)&base, (void*)&nb};
+        if (int rc = launch_dependent_params((const void*)&fts::k_bucket_sort<void>, (unsigned)((batch + fts::SORT_CHUNK - 1) / fts::SORT_CHUNK), 256, params, s)) return rc;
+        if (int rc = launch_dependent(fn_bucket, (unsigned)g_prop.multiProcessorCount * 2, 256, 0, &a, s)) return rc;
+    }
     if (fn_tail) {
         const long long cap = (long long)g_prop.multiProcessorCount * 8;
         if (int rc = launch_dependent(fn_tail, (unsigned)(batch < cap ? batch : cap), 256, 0, &a, s)) return rc;

@@ -54,6 +54,14 @@ struct Registrar {
     };                                                                                                               \
     static fts_host::Registrar k_tail_reg_##FUNCTOR(k_tail_entries_##FUNCTOR, 4);
 
+// bucket pass of the exp-table families (Float64): arbitrary parameter order in large 1D batches
+#define FTS_REGISTER_BUCKET(FAM, FUNCTOR)                                                                            \
+    static const fts_host::KernelEntry k_bucket_entries_##FUNCTOR[] = {                                             \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_BUCKET, 0, FTS_KPTR(fts::k_adaptive1d_bucket<double, fts::FUNCTOR, false>)},    \
+        {FAM, FTS_F64, fts_host::KID_ADAPT_BUCKET, 1, FTS_KPTR(fts::k_adaptive1d_bucket<double, fts::FUNCTOR, true>)},     \
+    };                                                                                                               \
+    static fts_host::Registrar k_bucket_reg_##FUNCTOR(k_bucket_entries_##FUNCTOR, 2);
+
 // reference-order cooperative kernels of a 2D / 3D family (CTA per integral, ordered sum), f32 + f64
 #define FTS_REGISTER_ORD(FAM, FUNCTOR, ORD_K)                                                            \
     static const fts_host::KernelEntry k_ord_entries_##FUNCTOR[] = {                                    \

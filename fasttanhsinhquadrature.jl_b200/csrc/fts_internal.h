@@ -23,7 +23,8 @@ enum KernelId : int {
     KID_EVAL = 8,          // k_eval1d                        pointwise integrand values (1D kinds)
     KID_FIXED_CMPL = 9,    // k_fixed1d_cmpl_tpi              integrate1D_cmpl (fixed grid, complement signature)
     KID_ADAPT_WARP = 10,   // k_adaptive2d_warp               warp per integral, shallow levels (large 2D batches, FAST only)
-    KID_COUNT = 11
+    KID_ADAPT_BUCKET = 11, // k_adaptive1d_bucket             warp tasks over bound-ordered chunks (1D exp families, Float64, arbitrary parameter order)
+    KID_COUNT = 12
 };
 
 struct KernelEntry {

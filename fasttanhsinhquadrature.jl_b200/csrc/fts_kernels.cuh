@@ -71,6 +71,15 @@ template <class T> struct Args {
     int tail_level;       // < 0: disabled
     int* tail_count;
     int* tail_idx;
+    // bucket passes of the 1D thread-per-integral call (k_bucket_sort, k_adaptive1d_bucket): a warp whose lanes
+    // would look up unrelated exp-table rows and stop at different levels (parameters in arbitrary order) does
+    // not compute; it leaves the float bits of its lanes' exp-argument bounds in sort_idx[b] and raises its bit
+    // sort_mask(b >> 5).  sort_ctl = {any warp queued, next warp task of k_adaptive1d_bucket}.
+    // sort_idx = nullptr: not armed.  Layout behind sort_idx (B = batch rounded up to SORT_CHUNK):
+    // keys[B], indices in bucket order per chunk (-1 behind the queued ones)[B], queued-warp flags[B / 32]
+    int* sort_ctl;
+    int* sort_idx;
+    int* sort_fb;         // pinned host word: the tail kernel stores sort_ctl[0] there (feedback for the next call); may be null
     // launch shape of the grouped 2D adaptive kernel (k_adaptive2d_cta): 0 = CTA per integral,
     // 32 = warp per integral with `level` as the deepest level a warp handles
     int group;
@@ -109,6 +118,11 @@ template <class T, class F> struct UsesLogTab { static constexpr bool value = De
 // flush before it reads the queue.  Both are no-ops for plain launches.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+constexpr int SORT_CHUNK = 1024;  // integrals one CTA of k_bucket_sort orders
+template <class T> __device__ __forceinline__ long long sort_padded(const Args<T>& a) { return (a.batch + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK; }
+template <class T> __device__ __forceinline__ int* sort_sorted(const Args<T>& a) { return a.sort_idx + sort_padded(a); }
+template <class T> __device__ __forceinline__ int* sort_mask(const Args<T>& a) { return a.sort_idx + 2 * sort_padded(a); }
 
 template <class T, class F> __device__ __forceinline__ void family_tables_init()
 {
@@ -374,7 +388,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(128) k_
 
 // levels of one integral; MODE selects the exp variant (shared-memory table, no range test)
 template <class T, class F, bool FAST, int MODE>
-__device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long long b, const T* p, T dx, T x0, bool neg, int flags)
+__device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long long b, const T* p, T dx, T x0, bool neg, int flags, int* q_count, int* q_idx)
 {
     const T half = num<T>::half();
     T h = a.tm * half;
@@ -436,7 +450,7 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
             break;
         }
         if (level == a.tail_level && level < a.max_levels) {  // park and let a whole CTA finish it
-            a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
+            q_idx[atomicAdd(q_count, 1)] = (int)b;
             a.value[b] = s_total;
             return;
         }
@@ -445,35 +459,71 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
 }
 
-template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_tpi(const Args<T> a)
+// quad() edge rules and the affine map of integral b with bounds (lo, hi); false: the result (zero width) has been stored
+template <class T, class F> __device__ __forceinline__ bool tpi_finish_prologue(const Args<T>& a, long long b, T lo, T hi, T& dx, T& x0, bool& neg, int& flags)
 {
-    pdl_launch_dependents();     // the tail kernel may be set up behind this grid's last wave
-    family_tables_init<T, F>();  // before any thread leaves (contains a barrier)
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.batch) return;
-    T p[F::NP > 0 ? F::NP : 1];
-    load_params<F::NP>(p, a, b);
     const T half = num<T>::half();
-    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
-    bool neg = false;
-    int flags = 0;
+    neg = false;
+    flags = 0;
     if (a.options & OPT_QUAD_EDGE) {
         if (!quad_edge_axis(lo, hi, neg)) {
             store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
-            return;
+            return false;
         }
         if (neg) flags |= FLAG_FLIPPED;
     }
-    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    dx = half * (hi - lo);
+    x0 = half * (hi + lo);
+    return true;
+}
+
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_tpi(const Args<T> a)
+{
+    pdl_launch_dependents();     // the kernels behind this one may be set up behind this grid's last wave
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = b < a.batch;
+    T p[F::NP > 0 ? F::NP : 1];
+    T lo = num<T>::zero(), hi = num<T>::zero();
+    if (mine) {                  // the loads of this integral's inputs fly while the CTA fills its tables
+        load_params<F::NP>(p, a, b);
+        lo = a.low[b * a.bstride];
+        hi = a.up[b * a.bstride];
+    }
+    family_tables_init<T, F>();  // before any thread leaves (contains a barrier)
+    if (!mine) return;
+    T dx, x0;
+    bool neg;
+    int flags;
+    if (!tpi_finish_prologue<T, F>(a, b, lo, hi, dx, x0, neg, flags)) return;
     if constexpr (UsesExpTab<T, F>::value) {
         // every exp argument of this integral is bounded by F::exp_arg_bound(|x0|+|dx|): below 700
         // the overflow/underflow test of exp is dead weight
-        if (F::template exp_arg_bound<T>(fm::abs(x0) + fm::abs(dx), p) < 700.0)
-            adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM | EXP_SAFE>(a, b, p, dx, x0, neg, flags);
+        const T bound = F::template exp_arg_bound<T>(fm::abs(x0) + fm::abs(dx), p);
+        if (a.sort_fb != nullptr) {
+            // Lanes whose bounds differ by more than ~1/4 look up unrelated rows of the shared exp table (an
+            // argument step of 1/4 is 46 rows: ~10 bank-conflict wavefronts per lookup instead of 1-2) and
+            // stop at different levels.  With the bucket passes armed (sort_idx) such a warp does not compute: it
+            // hands its integrals to them, which regroup them by bound; otherwise it only reports itself, so that
+            // the next call arms the passes.  A sorted sweep never gets here.
+            const int q = __double2int_rd(fmin((double)bound, 1.0e7) * 8.0);
+            const unsigned m = __activemask();
+            const bool queued = __reduce_max_sync(m, q) - __reduce_min_sync(m, q) > 2;
+            const bool leader = (int)(threadIdx.x & 31) == __ffs(m) - 1;
+            if (queued && leader) a.sort_ctl[0] = 1;
+            if (a.sort_idx != nullptr) {
+                if (leader) sort_mask(a)[b >> 5] = queued ? 1 : 0;
+                if (queued) {
+                    a.sort_idx[b] = __float_as_int(fminf(fmaxf((float)bound, 0.0f), 3.0e38f));
+                    return;
+                }
+            }
+        }
+        if (bound < 700.0)
+            adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM | EXP_SAFE>(a, b, p, dx, x0, neg, flags, a.tail_count, a.tail_idx);
         else
-            adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM>(a, b, p, dx, x0, neg, flags);
+            adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM>(a, b, p, dx, x0, neg, flags, a.tail_count, a.tail_idx);
     } else {
-        adaptive1d_tpi_levels<T, F, FAST, 0>(a, b, p, dx, x0, neg, flags);
+        adaptive1d_tpi_levels<T, F, FAST, 0>(a, b, p, dx, x0, neg, flags, a.tail_count, a.tail_idx);
     }
 }
 
@@ -568,11 +618,225 @@ template <class T> __device__ __forceinline__ void ordered_add(T& s, const T* te
     for (; i < m; ++i) s = s + terms[i];
 }
 
-// Deep levels of queued 1D integrals (see Args::tail_level): one CTA per integral.  The CTA
-// evaluates a tile of w_i*(f(x+)+f(x-)) terms in parallel into shared memory, then ONE thread adds
-// them in index order, so the result is bit-identical to the sequential reference loop
-// (adaptive.jl:55-60 / 763-770) while the integrand work is spread over 256 threads.
-// (Double64 tiles are tree-reduced instead, see below.)
+// one queued deep integral (see Args::tail_level), by the whole CTA
+template <class T, class F, bool FAST, bool CMPL> __device__ __forceinline__ void tail_integral(const Args<T>& a, long long b, T* terms, int* s_done)
+{
+    constexpr int TILE = 1024;
+    const int tid = threadIdx.x;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half(), one = num<T>::one();
+    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    bool neg = false;
+    int flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        quad_edge_axis(lo, hi, neg);
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    T h = a.tm * half;
+    for (int l = 0; l < a.tail_level; ++l) h = h * half;
+    T s_total = a.value[b];
+    T old_res = dx * h * s_total;
+    T err = num<T>::zero();
+    int level_used = a.tail_level;
+    for (int level = a.tail_level + 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 1 << level;
+        T s_new = num<T>::zero();
+        for (int t0 = 0; t0 < n; t0 += TILE) {
+            const int m = n - t0 < TILE ? n - t0 : TILE;
+            for (int i = tid; i < m; i += blockDim.x) {
+                if constexpr (CMPL) {
+                    const NodeC<T> nd = a.nodes_c[(n - 2) + t0 + i];
+                    const T dxck = dx * nd.c, dx1p = dx * (one + nd.x), d = dx * nd.x;
+                    terms[i] = nd.w * (F::template eval<T, FAST>(d + x0, dxck, dx1p, p) + F::template eval<T, FAST>(x0 - d, dx1p, dxck, p));
+                } else {
+                    const Node<T> nd = ldg_node(a.nodes + (n - 2) + t0 + i);
+                    const T d = dx * nd.x;
+                    terms[i] = nd.w * (F::template eval<T, FAST>(d + x0, p) + F::template eval<T, FAST>(x0 - d, p));
+                }
+            }
+            __syncthreads();
+            if constexpr (sizeof(T) == 16) {
+                // Double64: a dependent double-double add costs ~160 cycles, so the in-order sum of a
+                // level-16 integral (131 072 terms) alone takes 10 ms.  Nothing pins the summation
+                // order of Double64, the tolerance is 1e-28 against a 1e-32 format: the
+                // tile is reduced by a fixed tree (per-thread strided sums, then halving) instead.
+                T part = num<T>::zero();
+                for (int i = tid; i < m; i += blockDim.x) part = part + terms[i];
+                __syncthreads();
+                terms[tid] = part;
+                __syncthreads();
+                for (int half_n = blockDim.x >> 1; half_n > 0; half_n >>= 1) {
+                    if (tid < half_n) terms[tid] = terms[tid] + terms[tid + half_n];
+                    __syncthreads();
+                }
+                if (tid == 0) s_new = s_new + terms[0];
+            } else if (tid == 0) {
+                ordered_add(s_new, terms, m);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            s_total = s_total + s_new;
+            const T new_res = dx * h * s_total;
+            err = fm::abs(new_res - old_res);
+            level_used = level;
+            old_res = new_res;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
+            if (conv) flags |= FLAG_CONVERGED;
+            *s_done = conv ? 1 : 0;
+        }
+        __syncthreads();
+        if (*s_done) break;
+    }
+    if (tid == 0) {
+        if (!(flags & FLAG_CONVERGED)) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+    __syncthreads();
+}
+
+// ---- integrals in arbitrary parameter order --------------------------------------------------------
+// Warps of k_adaptive1d_tpi whose lanes held unrelated integrals left them alone (Args::sort_idx).
+// k_bucket_sort (one CTA per chunk of SORT_CHUNK integrals, any family / element type) orders the queued integrals
+// of its chunk by the exp-argument bound their warp stored: a counting sort into SORT_CHUNK buckets between the
+// chunk's smallest and largest bound, in shared memory.  k_adaptive1d_bucket then walks the ordered chunks with
+// one WARP per task of 32 consecutive entries (tasks are claimed from a counter: no CTA barrier in the level loop, a
+// warp that drew shallow integrals simply claims the next task): lanes of a warp now stop at the same level, and the
+// eight-copy exp table (EXP_SMEM8) makes their lookups conflict-free although their rows still differ.  Every
+// integral is computed by the same code as in the first kernel and writes to its own slot: results do not depend
+// on the order of the batch, bit for bit.  Integrals that are still unconverged at Args::tail_level join the deep
+// queue, which k_adaptive1d_tail (launched last) drains.
+template <class Tag> __global__ void __launch_bounds__(256) k_bucket_sort(const int* ctl, int* base, long long batch)
+{
+    __shared__ int hist[SORT_CHUNK];
+    __shared__ int sred[12];
+    pdl_launch_dependents();
+    pdl_wait_primary();
+    if (ctl[0] == 0) return;            // no warp queued anything: uniform over the grid
+    const long long padded = (batch + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    const int* keys = base;
+    int* sorted = base + padded;
+    const int* mask = base + 2 * padded;
+    const int tid = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * SORT_CHUNK;
+    constexpr int PER = SORT_CHUNK / 256;
+    float v[PER];
+    bool on[PER];
+    if (tid == 0) {
+        sred[8] = 0x7f7fffff;           // bits of the largest float
+        sred[9] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) hist[tid + 256 * k] = 0;
+    __syncthreads();
+    int lmin = 0x7f7fffff, lmax = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const long long i = c0 + tid + 256 * k;
+        on[k] = i < batch && mask[i >> 5] != 0;
+        v[k] = on[k] ? fminf(fmaxf(__int_as_float(keys[i]), 0.0f), 3.0e38f) : 0.0f;  // a lane that left before storing its key: any bucket will do
+        if (on[k]) {
+            lmin = min(lmin, __float_as_int(v[k]));  // the bits of a non-negative float are monotone in its value
+            lmax = max(lmax, __float_as_int(v[k]));
+        }
+    }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if ((tid & 31) == 0) {
+        atomicMin(&sred[8], lmin);
+        atomicMax(&sred[9], lmax);
+    }
+    __syncthreads();
+    const float vmin = __int_as_float(sred[8]), vmax = __int_as_float(sred[9]);
+    const float scale = vmax > vmin ? (float)(SORT_CHUNK - 1) / (vmax - vmin) : 0.0f;
+    int bucket[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+        if (on[k]) {
+            const int q = (int)((v[k] - vmin) * scale);
+            bucket[k] = q < 0 ? 0 : (q > SORT_CHUNK - 1 ? SORT_CHUNK - 1 : q);
+            atomicAdd(&hist[bucket[k]], 1);
+        }
+    __syncthreads();
+    {   // exclusive scan of the bucket counts: PER consecutive buckets per thread
+        int cnt[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            cnt[k] = hist[tid * PER + k];
+            sum += cnt[k];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((tid & 31) >= off) inc += o;
+        }
+        if ((tid & 31) == 31) sred[tid >> 5] = inc;
+        __syncthreads();
+        int before = inc - sum;
+        for (int w = 0; w < (tid >> 5); ++w) before += sred[w];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            hist[tid * PER + k] = before;
+            before += cnt[k];
+        }
+        if (tid == 255) sred[10] = before;  // queued integrals of the chunk
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if (on[k]) sorted[c0 + atomicAdd(&hist[bucket[k]], 1)] = (int)(c0 + tid + 256 * k);
+        if (tid + 256 * k >= sred[10]) sorted[c0 + tid + 256 * k] = -1;  // the entries behind the queued ones: nothing to do
+    }
+}
+
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_bucket(const Args<T> a)
+{
+    pdl_launch_dependents();
+    pdl_wait_primary();
+    if (a.sort_ctl[0] == 0) return;     // uniform over the grid
+    if constexpr (UsesExpTab<T, F>::value) {
+        exp_tab8_init();
+        const int ntasks = (int)(sort_padded(a) / 32);
+        const int* sorted = sort_sorted(a);
+        const int lane = threadIdx.x & 31;
+        // Task t = entries 32 t ... 32 t + 31 of the ordered chunks, claimed from a counter one at a time.  (Tried and
+        // dropped, profiles/r2_bucket_pass_experiments.md: claiming two tasks ahead so that the claim, the entry and the
+        // inputs of a task are in flight behind the arithmetic of the previous one — every warp then sits on two tasks
+        // when the counter runs out and the kernel ends 10 us later; dealing most tasks round-robin with cp.async
+        // input prefetch — faster alone under ncu, slower inside the back-to-back steps of bench.py.)
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(a.sort_ctl + 1, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= ntasks) break;
+            const int b = sorted[(long long)t * 32 + lane];
+            if (b >= 0) {
+                T p[F::NP > 0 ? F::NP : 1];
+                load_params<F::NP>(p, a, b);
+                T dx, x0;
+                bool neg;
+                int flags;
+                if (tpi_finish_prologue<T, F>(a, b, a.low[(long long)b * a.bstride], a.up[(long long)b * a.bstride], dx, x0, neg, flags)) {
+                    if (F::template exp_arg_bound<T>(fm::abs(x0) + fm::abs(dx), p) < 700.0)
+                        adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM8 | EXP_SAFE>(a, b, p, dx, x0, neg, flags, a.tail_count, a.tail_idx);
+                    else
+                        adaptive1d_tpi_levels<T, F, FAST, EXP_SMEM8>(a, b, p, dx, x0, neg, flags, a.tail_count, a.tail_idx);
+                }
+            }
+            __syncwarp();               // the claim is a full-warp shuffle
+        }
+    }
+}
+
+// Last kernel of a 1D thread-per-integral call (launched as a programmatic dependent of the previous one): the
+// deep queue — integrals that were still unconverged at Args::tail_level — finished one CTA each: the CTA
+// evaluates a tile of w_i*(f(x+)+f(x-)) terms in parallel into shared memory, then ONE thread adds them in index
+// order, so the result is bit-identical to the sequential reference loop (adaptive.jl:55-60 / 763-770) while the
+// integrand work is spread over 256 threads (Double64 tiles are tree-reduced instead, see tail_integral).
 template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bounds__(256) k_adaptive1d_tail(const Args<T> a)
 {
     family_tables_init<T, F>();
@@ -580,91 +844,18 @@ template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bound
     __shared__ T terms[TILE];
     __shared__ int s_done;
     const int tid = threadIdx.x;
-    pdl_wait_primary();  // the thread-per-integral kernel has completed: the queue is final and visible
+    pdl_wait_primary();  // the kernels before this one have completed: the queue is final and visible
     const int count = *a.tail_count;
-    for (int q = blockIdx.x; q < count; q += gridDim.x) {
-        const long long b = a.tail_idx[q];
-        T p[F::NP > 0 ? F::NP : 1];
-        load_params<F::NP>(p, a, b);
-        const T half = num<T>::half(), one = num<T>::one();
-        T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
-        bool neg = false;
-        int flags = 0;
-        if (a.options & OPT_QUAD_EDGE) {
-            quad_edge_axis(lo, hi, neg);
-            if (neg) flags |= FLAG_FLIPPED;
-        }
-        const T dx = half * (hi - lo), x0 = half * (hi + lo);
-        T h = a.tm * half;
-        for (int l = 0; l < a.tail_level; ++l) h = h * half;
-        T s_total = a.value[b];
-        T old_res = dx * h * s_total;
-        T err = num<T>::zero();
-        int level_used = a.tail_level;
-        for (int level = a.tail_level + 1; level <= a.max_levels; ++level) {
-            h = h * half;
-            const int n = 1 << level;
-            T s_new = num<T>::zero();
-            for (int t0 = 0; t0 < n; t0 += TILE) {
-                const int m = n - t0 < TILE ? n - t0 : TILE;
-                for (int i = tid; i < m; i += blockDim.x) {
-                    if constexpr (CMPL) {
-                        const NodeC<T> nd = a.nodes_c[(n - 2) + t0 + i];
-                        const T dxck = dx * nd.c, dx1p = dx * (one + nd.x), d = dx * nd.x;
-                        terms[i] = nd.w * (F::template eval<T, FAST>(d + x0, dxck, dx1p, p) + F::template eval<T, FAST>(x0 - d, dx1p, dxck, p));
-                    } else {
-                        const Node<T> nd = ldg_node(a.nodes + (n - 2) + t0 + i);
-                        const T d = dx * nd.x;
-                        terms[i] = nd.w * (F::template eval<T, FAST>(d + x0, p) + F::template eval<T, FAST>(x0 - d, p));
-                    }
-                }
-                __syncthreads();
-                if constexpr (sizeof(T) == 16) {
-                    // Double64: a dependent double-double add costs ~160 cycles, so the in-order sum of a
-                    // level-16 integral (131 072 terms) alone takes 10 ms.  Nothing pins the summation
-                    // order of Double64, the tolerance is 1e-28 against a 1e-32 format: the
-                    // tile is reduced by a fixed tree (per-thread strided sums, then halving) instead.
-                    T part = num<T>::zero();
-                    for (int i = tid; i < m; i += blockDim.x) part = part + terms[i];
-                    __syncthreads();
-                    terms[tid] = part;
-                    __syncthreads();
-                    for (int half_n = blockDim.x >> 1; half_n > 0; half_n >>= 1) {
-                        if (tid < half_n) terms[tid] = terms[tid] + terms[tid + half_n];
-                        __syncthreads();
-                    }
-                    if (tid == 0) s_new = s_new + terms[0];
-                } else if (tid == 0) {
-                    ordered_add(s_new, terms, m);
-                }
-                __syncthreads();
-            }
-            if (tid == 0) {
-                s_total = s_total + s_new;
-                const T new_res = dx * h * s_total;
-                err = fm::abs(new_res - old_res);
-                level_used = level;
-                old_res = new_res;
-                const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
-                if (conv) flags |= FLAG_CONVERGED;
-                s_done = conv ? 1 : 0;
-            }
-            __syncthreads();
-            if (s_done) break;
-        }
-        if (tid == 0) {
-            if (!(flags & FLAG_CONVERGED)) flags |= FLAG_MAX_LEVELS;
-            store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
-        }
-        __syncthreads();
-    }
-    // the last CTA to leave re-arms the (persistent, per-stream) queue for the next launch
+    for (int q = blockIdx.x; q < count; q += gridDim.x) tail_integral<T, F, FAST, CMPL>(a, a.tail_idx[q], terms, &s_done);
+    // the last CTA to leave re-arms the (persistent, per-stream) queues for the next launch
     if (tid == 0) {
         __threadfence();
         const unsigned int t = atomicAdd(a.ticket, 1u);
         if (t == gridDim.x - 1) {
             *a.tail_count = 0;
             *a.ticket = 0u;
+            if (a.sort_fb) *a.sort_fb = a.sort_ctl[0];
+            if (a.sort_ctl) a.sort_ctl[0] = a.sort_ctl[1] = 0;
         }
     }
 }

@@ -147,6 +147,54 @@ def test_config_b_against_oracle(gpu, oracle):
     assert np.array_equal(rp.value, r.value[perm]) and np.array_equal(rp.levels, r.levels[perm]) and np.array_equal(rp.err, r.err[perm])
 
 
+def test_bucket_pass_with_deep_integrals(gpu, oracle):
+    """Arbitrary parameter order with a wide parameter range: incoherent warps of k_adaptive1d_tpi leave their
+    integrals to k_bucket_sort (counting sort by exp-argument bound per chunk) and k_adaptive1d_bucket (warp tasks
+    over the ordered chunks, eight-copy exp table); integrals still unconverged at level 8 join the deep queue of
+    k_adaptive1d_tail.  Every integral must come out exactly as in a coherent (sorted) batch and as the oracle
+    computes it.  Pinned buffers: the kernels work on the whole batch in place (pageable arrays are cut into chunks
+    below the size at which the passes are armed)."""
+    from fts_b200 import _lib as L
+    n = 1 << 18
+    a_sorted = np.exp(np.linspace(np.log(0.5), np.log(2.0e5), n))   # stop levels 4 ... 11: the deep ones leave through the tail
+    perm = np.random.default_rng(3).permutation(n)
+    cache = gpu.adaptive_cache_1D(np.float64, max_levels=16)
+    f = gpu.builtin("gauss")
+    lo, hi, al = gpu.pinned_empty(1), gpu.pinned_empty(1), gpu.pinned_empty(n)
+    v, e, lv, fl = gpu.pinned_empty(n), gpu.pinned_empty(n), gpu.pinned_empty(n, np.int32), gpu.pinned_empty(n, np.int32)
+    lo[...], hi[...] = -1.0, 1.0
+
+    def run(alpha, m=n):
+        al[:m] = alpha
+        before = gpu.launch_count()
+        gpu.adaptive_batch_host(cache, f, low=lo.ctypes.data, up=hi.ctypes.data, bounds_stride=0, params=al.ctypes.data, params_stride=1,
+                                rtol=1e-10, atol=0.0, max_levels=16, batch=m, value=v.ctypes.data, err=e.ctypes.data, levels=lv.ctypes.data,
+                                flags=fl.ctypes.data, order="reference", options=L.OPT_QUAD_EDGE_RULES)
+        return (v[:m].copy(), e[:m].copy(), lv[:m].copy(), fl[:m].copy()), gpu.launch_count() - before
+
+    # the passes are armed by feedback from the previous call on the stream: the first shuffled call computes every
+    # integral where it lies and reports its incoherent warps, the second one goes through the passes
+    a_coherent = _alpha(n)          # neighbours 2e-4 apart: no warp reports itself
+    run(a_coherent)
+    _, k0 = run(a_coherent)
+    r1, k1 = run(a_sorted[perm])
+    r2, k2 = run(a_sorted[perm])
+    rs, _ = run(a_sorted)           # sorted, but neighbours at the upper end are several units apart: still through the passes
+    _, kc1 = run(a_coherent)
+    _, kc2 = run(a_coherent)
+    assert (k0, k1, k2, kc1, kc2) == (2, 2, 4, 4, 2), (k0, k1, k2, kc1, kc2)  # tpi + tail | tpi + sort + bucket + tail
+    for x1, x2, y in zip(r1, r2, rs):
+        assert np.array_equal(x1, x2) and np.array_equal(x2, y[perm])
+    assert r2[2].max() >= 10 and (r2[3] & L.FLAG_CONVERGED).all()
+    # a small batch (below the size at which the passes exist) gives the same bits
+    sub = np.random.default_rng(4).choice(n, 20000, replace=False)
+    r3, k3 = run(a_sorted[perm][sub], 20000)
+    assert k3 == 2 and all(np.array_equal(x3, x2[sub]) for x3, x2 in zip(r3, r2))
+    ref = oracle.batch_adaptive1d("f64", F["F1_GAUSS"], a_sorted[perm], [-1.0], [1.0], 1e-10, 0.0, 16, oracle.cache1d("f64", 16))
+    same = r2[2] == ref["level"]
+    assert same.mean() > 0.999 and rel(r2[0][same], ref["value"][same]).max() <= RTOL64
+
+
 def test_config_b_full_size_properties(gpu):
     """2^20 integrals (BASELINE size): permutation invariance (each integral is independent of its
     position in the batch -> bit-identical after un-permuting), closed form, evaluation count."""
