@@ -318,6 +318,11 @@ def sharded3d_record(fts, dev, world, rank, dist, levels, reps: int):
                     dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
                     rec[arm]["exchange_wait_us_per_level_rank0"] = [round(x / 1e3, 2) for x in w.cpu().tolist()]
                     rec[arm]["exchange_wait_us_per_level_max_over_ranks"] = [round(x / 1e3, 2) for x in wmax.cpu().tolist()]
+                if arm in ("single", "fused_peer"):
+                    # device globaltimer at each level's stop test (last repetition): where the call's time goes per level
+                    done = plan.level_done_ns().astype(np.int64)
+                    if done.size > 1 and done.min() > 0:
+                        rec[arm]["level_us_rank0"] = [round(float(x) / 1e3, 2) for x in np.diff(done)]
             exact = (math.e - 1 / math.e) ** 3 if fam == "exp_3d" else (2 * math.log(2) - 2) ** 3
             rec["rel_err_vs_closed_form"] = abs(rec["single"]["value"] - exact) / abs(exact)
             for arm in ("fused_peer", "nccl_allgather"):

@@ -1100,6 +1100,13 @@ static int launch_level(const void* fn, fts_cache c, int dim, bool cmpl, const T
     return launch_raw(fn, grid_level_blocks(dim, level, nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s);
 }
 
+// FTS_B200_STEP_FUSED=0: the two-launch form (level kernel, then a one-warp stop-test kernel) for A/B runs
+static bool step_in_level_kernel()
+{
+    static const bool v = [] { const char* e = getenv("FTS_B200_STEP_FUSED"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+
 template <class T, int D> static void launch_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks, const T* partials, T* state, cudaStream_t s, int options = 0, int max_levels = 0)
 {
     fts::k_sharded_step<T, D><<<1, 1, 0, s>>>(low, up, tm, rtol, atol, level, nranks, partials, state, options, max_levels);
@@ -1125,11 +1132,29 @@ static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int o
     unsigned int* ticket = (unsigned int*)(state + 8);
     FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
     const T tm = load_elem<T>(c->tm);
+    const bool one_launch = step_in_level_kernel();
     for (long long b = 0; b < batch; ++b) {
         const T* lo = low + b * bstride;
         const T* hi = up + b * bstride;
         const T* pp = params ? params + b * pstride : nullptr;
         for (int level = 0; level <= max_levels; ++level) {
+            if (one_launch) {  // stop test in the last CTA of the level kernel, one-CTA levels in one launch
+                fts::Args<T> a;
+                memset(&a, 0, sizeof a);
+                fill_cache_args(a, c);
+                a.low = lo; a.up = hi; a.params = pp; a.bstride = dim; a.pstride = 0; a.batch = 1;
+                a.level = level; a.rank = 0; a.nranks = 1;
+                a.block_partials = block_partials; a.ticket = ticket; a.partial_out = partial; a.state = level ? state : nullptr;
+                const unsigned blocks = grid_level_blocks(dim, level, 1);
+                int top = level;
+                if (blocks == 1)
+                    while (top < max_levels && grid_level_blocks(dim, top + 1, 1) == 1) ++top;
+                a.step_fused = 1; a.level_hi = top; a.state_out = state;
+                a.rtol = rtol; a.atol = atol; a.options = options; a.max_levels = max_levels;
+                if (int rc = launch_raw(fn, blocks, fts::CTA_THREADS, grid_level_smem(dim, cmpl, top, sizeof(T)), &a, s)) return rc;
+                level = top;
+                continue;
+            }
             if (int rc = launch_level<T>(fn, c, dim, cmpl, lo, hi, pp, level, 0, 1, block_partials, ticket, partial, level ? state : nullptr, s)) return rc;
             if (dim == 3) launch_step<T, 3>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options, max_levels);
             else launch_step<T, 2>(lo, hi, tm, rtol, atol, level, 1, partial, state, s, options, max_levels);
@@ -1610,6 +1635,7 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
     const unsigned long long tmo = peer_timeout_ns();
     const T tm = load_elem<T>(c->tm);
     const int parity = ((long long)epoch) & 1;
+    const bool one_launch = step_in_level_kernel();
     for (int level = 0; level <= max_levels; ++level) {
         const bool shard = mailboxes != nullptr && level >= shard_from;  // nranks == 1 with a mailbox exercises the flag protocol on one GPU
         fts::Args<T> a;
@@ -1623,7 +1649,21 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
             a.mail_slot = parity * 64 + level;
             a.epoch = epoch;
         }
-        if (int rc = launch_raw(fn, grid_level_blocks(dim, level, a.nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s)) return rc;
+        const unsigned blocks = grid_level_blocks(dim, level, a.nranks);
+        if (one_launch) {
+            // exchange wait + stop test in the last CTA of the level kernel; the levels that fit one CTA (and
+            // agree on sharded / not sharded) are walked by that CTA in ONE launch
+            int hi = level;
+            if (blocks == 1)
+                while (hi < max_levels && grid_level_blocks(dim, hi + 1, a.nranks) == 1 && (mailboxes != nullptr && hi + 1 >= shard_from) == shard) ++hi;
+            a.step_fused = 1; a.level_hi = hi; a.state_out = state;
+            a.rtol = rtol; a.atol = atol; a.options = options; a.max_levels = max_levels;
+            a.timeout_ns = tmo; a.wait_ns = g_peer_wait;
+            if (int rc = launch_raw(fn, blocks, fts::CTA_THREADS, grid_level_smem(dim, cmpl, hi, sizeof(T)), &a, s)) return rc;
+            level = hi;
+            continue;
+        }
+        if (int rc = launch_raw(fn, blocks, fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s)) return rc;
         if (shard) {
             if (dim == 3) fts::k_sharded_step_fused<T, 3><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait, max_levels);
             else fts::k_sharded_step_fused<T, 2><<<1, 32, 0, s>>>(low, up, tm, rtol, atol, level, nranks, (const double*)mailboxes[rank], a.mail_slot, epoch, state, options, tmo, g_peer_wait, max_levels);

@@ -86,8 +86,16 @@ template <class T> struct Args {
     // fused exchange over NVLink peer memory (k_level_grid epilogue): the last CTA stores this
     // rank's (s, c) and then the epoch flag straight into every rank's mailbox
     double* peer_mail[FTS_MAX_RANKS];  // mailbox of rank r mapped into this process (own one included); null: no exchange
-    int mail_slot;                     // index of this launch's slot row: (epoch&1)*levels + level
+    int mail_slot;                     // index of this launch's slot row: (epoch&1)*levels + level (of a.level; +1 per level of a range)
     double epoch;                      // flag value of this call
+    // stop test in the epilogue of k_level_grid (step_fused != 0): the last CTA of the launch waits for the peers'
+    // partials (if any), updates state_out like k_sharded_step and leaves; level_hi > level: one CTA walks the
+    // levels level ... level_hi in one launch (the levels that are one CTA small)
+    int step_fused;
+    int level_hi;
+    T* state_out;
+    unsigned long long timeout_ns;     // peer wait limit
+    unsigned long long* wait_ns;       // [64] or null: [level] exchange wait, [32 + level] globaltimer when the level's stop test was done
 };
 
 template <int NP, class T> __device__ __forceinline__ void load_params(T (&p)[NP > 0 ? NP : 1], const Args<T>& a, long long b)

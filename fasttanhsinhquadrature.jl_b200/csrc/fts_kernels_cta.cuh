@@ -933,6 +933,89 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fix
     if (tid == 0) a.value[b] = (s.dx * s.dy * s.dz * (a.h * a.h * a.h)) * tot.value();
 }
 
+// Stop test after the partials of all ranks are known (adaptive.jl:693-700): one thread, identical arithmetic
+// on every rank.  part(r) = rank r's compensated (s, c) of the level, merged in rank order.
+// state = {s_total.s, s_total.c, old_res, value, err, done, level_used, h}
+// state[5] (done): 0 running, 1 converged, 2 zero-width box under the quad() edge rules, 3 a peer never delivered.
+template <class T, int D, class Part>
+__device__ __forceinline__ void level_step_apply(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks, Part part, T* state, int options, int max_levels)
+{
+    if (level == 0 && (options & OPT_QUAD_EDGE)) {  // any(low .== up) -> zero(T)   quad.jl:96-98,129-131
+        bool zero = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) zero = zero || (low[d] == up[d]);
+        if (zero) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) state[i] = num<T>::zero();
+            state[5] = num<T>::from_double(2.0);
+            return;
+        }
+    }
+    const T half = num<T>::half();
+    Comp<T> tot;
+    if (level > 0) {
+        tot.s = state[0];
+        tot.c = state[1];
+    }
+    for (int r = 0; r < nranks; ++r) tot.merge(part(r));
+    T scale = num<T>::one();
+#pragma unroll
+    for (int d = 0; d < D; ++d) scale = scale * (half * (up[d] - low[d]));
+    const T h = level == 0 ? tm * half : state[7] * half;
+    T hD = h;
+#pragma unroll
+    for (int d = 1; d < D; ++d) hD = hD * h;
+    const T res = scale * hD * tot.value();
+    state[0] = tot.s;
+    state[1] = tot.c;
+    state[7] = h;
+    state[6] = num<T>::from_double((double)level);
+    if (level == 0) {
+        state[2] = res;
+        state[3] = res;
+        state[4] = num<T>::zero();
+        state[5] = num<T>::zero();
+    } else {
+        const T err = fm::abs(res - state[2]);
+        state[2] = res;
+        state[3] = res;
+        state[4] = err;
+        if (err <= fm::err_target(res, rtol, atol) && may_stop(options, level, max_levels)) state[5] = num<T>::one();
+    }
+}
+
+// lanes 0 .. nranks-1 of a warp wait for the peers' flags of `slot_row` in this rank's own mailbox; returns false
+// on timeout; *waited_ns = the longest wait
+__device__ __forceinline__ bool peer_wait_flags(const double* mail, int slot_row, int nranks, double epoch, unsigned long long timeout_ns, unsigned long long* waited_ns)
+{
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+    unsigned long long waited = 0ULL;
+    if (lane < nranks) {
+        const volatile double* slot = mail + ((size_t)slot_row * nranks + lane) * 4;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        t1 = t0;
+        while (slot[2] != epoch) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                ok = false;
+                break;
+            }
+        }
+        waited = t1 - t0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, waited, off);
+        waited = o > waited ? o : waited;
+    }
+    *waited_ns = __shfl_sync(0xffffffffu, waited, 0);
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    return ok;
+}
+
 // ------------------------------------------------------------------ one level, whole grid ----
 // Partial sum of level `a.level` (0 = base grid) of ONE 2D/3D integral (bounds/params at index
 // 0), flat new-cell index dealt over gridDim.x CTAs and a.nranks devices.  The last CTA to
@@ -951,228 +1034,170 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
     const long long gthreads = (long long)gridDim.x * blockDim.x;
     const long long start = (long long)a.rank * gthreads + (long long)blockIdx.x * blockDim.x + tid;
     const long long stride = gthreads * a.nranks;
-    const int level = a.level;
-    const int n = level == 0 ? 2 : (2 << level);
-    T acc;
-    if constexpr (D == 3) {
-        Sm3<T> s;
-        s.dx = half * (a.up[0] - a.low[0]); s.x0 = half * (a.up[0] + a.low[0]);
-        s.dy = half * (a.up[1] - a.low[1]); s.y0 = half * (a.up[1] + a.low[1]);
-        s.dz = half * (a.up[2] - a.low[2]); s.z0 = half * (a.up[2] + a.low[2]);
-        s.w0 = num<T>::half_pi();
-        sm3_carve<T>(s, reinterpret_cast<T*>(fts_dyn_smem), n);
-        if (level == 0) sm3_stage<T>(s, a.ix, a.iw, 1, 2);
-        else { const Node<T>* lv = a.nodes + (n - 4); sm3_stage<T>(s, &lv->x, &lv->w, 2, n); }
-        __syncthreads();
-        acc = level_sum_3d<T, F>(s, p, n, level + 1, level == 0, start, stride);
-        if (level == 0 && start == 0) acc = acc + (s.w0 * s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.z0, p);
-    } else {
-        Sm2<T> s;
-        s.dx = half * (a.up[0] - a.low[0]); s.x0 = half * (a.up[0] + a.low[0]);
-        s.dy = half * (a.up[1] - a.low[1]); s.y0 = half * (a.up[1] + a.low[1]);
-        s.w0 = num<T>::half_pi();
-        sm2_carve<T, CMPL>(s, reinterpret_cast<T*>(fts_dyn_smem), n);
-        if (level == 0) sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2);
-        else if constexpr (CMPL) { const NodeC<T>* lv = a.nodes_c + (n - 4); sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n); }
-        else { const Node<T>* lv = a.nodes + (n - 4); sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n); }
-        __syncthreads();
-        acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, level == 0, start, stride);
-        if (level == 0 && start == 0) {
-            if constexpr (CMPL) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.dx, s.dx, s.dy, s.dy, p);
-            else {
-                if constexpr (D == 2) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
+    const int level_hi = a.step_fused ? a.level_hi : a.level;
+    for (int level = a.level; level <= level_hi; ++level) {
+        if (a.step_fused && level > 0) {  // converged at an earlier level (this call: state_out is only written by last CTAs)
+            if (__ldcg(a.state_out + 5) != num<T>::zero()) {
+                if (a.wait_ns && blockIdx.x == 0 && tid == 0) a.wait_ns[level] = 0ULL;
+                return;
             }
         }
-    }
-    const Comp<T> bsum = block_reduce(comp_of(acc), red);
-    if (tid == 0) {
-        a.block_partials[2 * blockIdx.x] = bsum.s;
-        a.block_partials[2 * blockIdx.x + 1] = bsum.c;
+        const int n = level == 0 ? 2 : (2 << level);
+        T acc;
+        if constexpr (D == 3) {
+            Sm3<T> s;
+            s.dx = half * (a.up[0] - a.low[0]); s.x0 = half * (a.up[0] + a.low[0]);
+            s.dy = half * (a.up[1] - a.low[1]); s.y0 = half * (a.up[1] + a.low[1]);
+            s.dz = half * (a.up[2] - a.low[2]); s.z0 = half * (a.up[2] + a.low[2]);
+            s.w0 = num<T>::half_pi();
+            sm3_carve<T>(s, reinterpret_cast<T*>(fts_dyn_smem), n);
+            if (level == 0) sm3_stage<T>(s, a.ix, a.iw, 1, 2);
+            else { const Node<T>* lv = a.nodes + (n - 4); sm3_stage<T>(s, &lv->x, &lv->w, 2, n); }
+            __syncthreads();
+            acc = level_sum_3d<T, F>(s, p, n, level + 1, level == 0, start, stride);
+            if (level == 0 && start == 0) acc = acc + (s.w0 * s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.z0, p);
+        } else {
+            Sm2<T> s;
+            s.dx = half * (a.up[0] - a.low[0]); s.x0 = half * (a.up[0] + a.low[0]);
+            s.dy = half * (a.up[1] - a.low[1]); s.y0 = half * (a.up[1] + a.low[1]);
+            s.w0 = num<T>::half_pi();
+            sm2_carve<T, CMPL>(s, reinterpret_cast<T*>(fts_dyn_smem), n);
+            if (level == 0) sm2_stage<T, CMPL>(s, a.ix, a.iw, a.ic, 1, 2);
+            else if constexpr (CMPL) { const NodeC<T>* lv = a.nodes_c + (n - 4); sm2_stage<T, CMPL>(s, &lv->x, &lv->w, &lv->c, 4, n); }
+            else { const Node<T>* lv = a.nodes + (n - 4); sm2_stage<T, CMPL>(s, &lv->x, &lv->w, nullptr, 2, n); }
+            __syncthreads();
+            acc = level_sum_2d<T, F, CMPL>(s, p, n, level + 1, level == 0, start, stride);
+            if (level == 0 && start == 0) {
+                if constexpr (CMPL) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.dx, s.dx, s.dy, s.dy, p);
+                else {
+                    if constexpr (D == 2) acc = acc + (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
+                }
+            }
+        }
+        const Comp<T> bsum = block_reduce(comp_of(acc), red);
+        if (tid == 0) {
+            a.block_partials[2 * blockIdx.x] = bsum.s;
+            a.block_partials[2 * blockIdx.x + 1] = bsum.c;
+            __threadfence();
+            const unsigned int t = atomicAdd(a.ticket, 1u);
+            s_last = (t == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
         __threadfence();
-        const unsigned int t = atomicAdd(a.ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    Comp<T> tot;
-    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
-        Comp<T> o;
-        o.s = __ldcg(a.block_partials + 2 * i);
-        o.c = __ldcg(a.block_partials + 2 * i + 1);
-        tot.merge(o);
-    }
-    tot = block_reduce(tot, red);
-    if (tid == 0) {
-        a.partial_out[0] = tot.s;
-        a.partial_out[1] = tot.c;
-        *a.ticket = 0u;
-    }
-    // fused all-gather: one lane per destination rank writes {s, c} into that rank's mailbox over
-    // NVLink (or locally for r == rank), fences system-wide, then raises the epoch flag
-    if (a.peer_mail[0] != nullptr && tid < a.nranks) {
-        const double s_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.s, 0));
-        const double c_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.c, 0));
-        volatile double* slot = a.peer_mail[tid] + ((size_t)a.mail_slot * a.nranks + a.rank) * 4;
-        slot[0] = s_;
-        slot[1] = c_;
-        __threadfence_system();
-        slot[2] = a.epoch;
+        Comp<T> tot;
+        for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+            Comp<T> o;
+            o.s = __ldcg(a.block_partials + 2 * i);
+            o.c = __ldcg(a.block_partials + 2 * i + 1);
+            tot.merge(o);
+        }
+        tot = block_reduce(tot, red);
+        if (tid == 0) {
+            a.partial_out[0] = tot.s;
+            a.partial_out[1] = tot.c;
+            *a.ticket = 0u;
+        }
+        const bool exchange = a.peer_mail[0] != nullptr;
+        const int slot_row = a.mail_slot + (level - a.level);
+        // fused all-gather: one lane per destination rank writes {s, c} into that rank's mailbox over
+        // NVLink (or locally for r == rank), fences system-wide, then raises the epoch flag
+        if (exchange && tid < a.nranks) {
+            const double s_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.s, 0));
+            const double c_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.c, 0));
+            volatile double* slot = a.peer_mail[tid] + ((size_t)slot_row * a.nranks + a.rank) * 4;
+            slot[0] = s_;
+            slot[1] = c_;
+            __threadfence_system();
+            slot[2] = a.epoch;
+        }
+        if (!a.step_fused) return;
+        // stop test (k_sharded_step / k_sharded_step_fused as an epilogue: no second launch per level)
+        if (tid < 32) {
+            bool ok = true;
+            unsigned long long waited = 0ULL;
+            const double* mail = a.peer_mail[a.rank];
+            if (exchange) ok = peer_wait_flags(mail, slot_row, a.nranks, a.epoch, a.timeout_ns, &waited);
+            if (tid == 0) {
+                if (!ok) a.state_out[5] = num<T>::from_double(3.0);
+                else if (exchange)
+                    level_step_apply<T, D>(a.low, a.up, a.tm, a.rtol, a.atol, level, a.nranks,
+                                           [&](int r) {
+                                               const volatile double* slot = mail + ((size_t)slot_row * a.nranks + r) * 4;
+                                               Comp<T> o;
+                                               o.s = num<T>::from_double(slot[0]);
+                                               o.c = num<T>::from_double(slot[1]);
+                                               return o;
+                                           },
+                                           a.state_out, a.options, a.max_levels);
+                else
+                    level_step_apply<T, D>(a.low, a.up, a.tm, a.rtol, a.atol, level, 1, [&](int) { return tot; }, a.state_out, a.options, a.max_levels);
+                if (a.wait_ns) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    a.wait_ns[level] = waited;
+                    if (level < 32) a.wait_ns[32 + level] = now;
+                }
+                __threadfence();
+            }
+        }
+        __syncthreads();  // a range of levels is walked by ONE CTA: the next level re-stages shared memory and reads the state
     }
 }
 
-// Stop test of the fused path: lane r of one warp waits for rank r's flag in OUR mailbox (peers
-// write it through NVLink), then thread 0 does the arithmetic of k_sharded_step.  A rank that never
-// arrives trips the timeout (FTS_B200_PEER_TIMEOUT_MS, default 10 s: host-side skew between ranks —
-// first-call module loads, a garbage collection — must not look like a dead peer) -> state[5] = 3 and
-// every later launch of the call exits.
+// Stop test of the two-launch fused path (FTS_B200_STEP_FUSED=0; the default does this in the epilogue of
+// k_level_grid): lane r of one warp waits for rank r's flag in OUR mailbox (peers write it through NVLink),
+// then thread 0 does the arithmetic of k_sharded_step.  A rank that never arrives trips the timeout
+// (FTS_B200_PEER_TIMEOUT_MS, default 10 s: host-side skew between ranks — first-call module loads, a garbage
+// collection — must not look like a dead peer) -> state[5] = 3 and every later launch of the call exits.
 template <class T, int D> __global__ void k_sharded_step_fused(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
                                                                const double* mail, int mail_slot, double epoch, T* state, int options,
                                                                unsigned long long timeout_ns, unsigned long long* wait_ns, int max_levels)
 {
-    __shared__ int s_ok;
     if (level > 0 && state[5] != num<T>::zero()) {
         if (wait_ns && threadIdx.x == 0) wait_ns[level] = 0ULL;
         return;
     }
-    const int lane = threadIdx.x;
-    if (lane == 0) s_ok = 1;
-    __syncwarp();
-    unsigned long long waited = 0ULL;
-    if (lane < nranks) {
-        const volatile double* slot = mail + ((size_t)mail_slot * nranks + lane) * 4;
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        t1 = t0;
-        while (slot[2] != epoch) {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > timeout_ns) {
-                s_ok = 0;
-                break;
-            }
-        }
-        waited = t1 - t0;
-    }
     // time this rank spent waiting for the slowest peer's flag (0 when every flag was already there):
     // the per-level exchange wait bench.py reports for the sharded 3D integral
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_down_sync(0xffffffffu, waited, off);
-        waited = o > waited ? o : waited;
+    unsigned long long waited = 0ULL;
+    const bool ok = peer_wait_flags(mail, mail_slot, nranks, epoch, timeout_ns, &waited);
+    if (threadIdx.x != 0) return;
+    if (wait_ns) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        wait_ns[level] = waited;
+        if (level < 32) wait_ns[32 + level] = now;
     }
-    if (wait_ns && lane == 0) wait_ns[level] = waited;
-    __syncwarp();
-    __threadfence_system();
-    if (lane != 0) return;
-    if (!s_ok) {
+    if (!ok) {
         state[5] = num<T>::from_double(3.0);
         return;
     }
-    if (level == 0 && (options & OPT_QUAD_EDGE)) {
-        bool zero = false;
-#pragma unroll
-        for (int d = 0; d < D; ++d) zero = zero || (low[d] == up[d]);
-        if (zero) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) state[i] = num<T>::zero();
-            state[5] = num<T>::from_double(2.0);
-            return;
-        }
-    }
-    const T half = num<T>::half();
-    Comp<T> tot;
-    if (level > 0) {
-        tot.s = state[0];
-        tot.c = state[1];
-    }
-    for (int r = 0; r < nranks; ++r) {
-        const volatile double* slot = mail + ((size_t)mail_slot * nranks + r) * 4;
-        Comp<T> o;
-        o.s = num<T>::from_double(slot[0]);
-        o.c = num<T>::from_double(slot[1]);
-        tot.merge(o);
-    }
-    T scale = num<T>::one();
-#pragma unroll
-    for (int d = 0; d < D; ++d) scale = scale * (half * (up[d] - low[d]));
-    const T h = level == 0 ? tm * half : state[7] * half;
-    T hD = h;
-#pragma unroll
-    for (int d = 1; d < D; ++d) hD = hD * h;
-    const T res = scale * hD * tot.value();
-    state[0] = tot.s;
-    state[1] = tot.c;
-    state[7] = h;
-    state[6] = num<T>::from_double((double)level);
-    if (level == 0) {
-        state[2] = res;
-        state[3] = res;
-        state[4] = num<T>::zero();
-        state[5] = num<T>::zero();
-    } else {
-        const T err = fm::abs(res - state[2]);
-        state[2] = res;
-        state[3] = res;
-        state[4] = err;
-        if (err <= fm::err_target(res, rtol, atol) && may_stop(options, level, max_levels)) state[5] = num<T>::one();
-    }
+    level_step_apply<T, D>(low, up, tm, rtol, atol, level, nranks,
+                           [&](int r) {
+                               const volatile double* slot = mail + ((size_t)mail_slot * nranks + r) * 4;
+                               Comp<T> o;
+                               o.s = num<T>::from_double(slot[0]);
+                               o.c = num<T>::from_double(slot[1]);
+                               return o;
+                           },
+                           state, options, max_levels);
 }
 
-// Stop test after the partials of all ranks are known (adaptive.jl:693-700): one thread,
-// identical arithmetic on every rank.  partials = [nranks][2] (s, c) in rank order.
-// state = {s_total.s, s_total.c, old_res, value, err, done, level_used, h}
-// state[5] (done): 0 running, 1 converged, 2 zero-width box under the quad() edge rules.
+// Stop test with the partials of all ranks in device memory (the caller exchanged them: NCCL all-gather, or
+// one rank): partials = [nranks][2] (s, c) in rank order.
 template <class T, int D> __global__ void k_sharded_step(const T* low, const T* up, T tm, T rtol, T atol, int level, int nranks,
                                                          const T* partials, T* state, int options, int max_levels)
 {
     if (level > 0 && state[5] != num<T>::zero()) return;
-    if (level == 0 && (options & OPT_QUAD_EDGE)) {  // any(low .== up) -> zero(T)   quad.jl:96-98,129-131
-        bool zero = false;
-#pragma unroll
-        for (int d = 0; d < D; ++d) zero = zero || (low[d] == up[d]);
-        if (zero) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) state[i] = num<T>::zero();
-            state[5] = num<T>::from_double(2.0);
-            return;
-        }
-    }
-    const T half = num<T>::half();
-    Comp<T> tot;
-    if (level > 0) {
-        tot.s = state[0];
-        tot.c = state[1];
-    }
-    for (int r = 0; r < nranks; ++r) {
-        Comp<T> o;
-        o.s = partials[2 * r];
-        o.c = partials[2 * r + 1];
-        tot.merge(o);
-    }
-    T scale = num<T>::one();
-#pragma unroll
-    for (int d = 0; d < D; ++d) scale = scale * (half * (up[d] - low[d]));
-    const T h = level == 0 ? tm * half : state[7] * half;
-    T hD = h;
-#pragma unroll
-    for (int d = 1; d < D; ++d) hD = hD * h;
-    const T res = scale * hD * tot.value();
-    state[0] = tot.s;
-    state[1] = tot.c;
-    state[7] = h;
-    state[6] = num<T>::from_double((double)level);
-    if (level == 0) {
-        state[2] = res;
-        state[3] = res;
-        state[4] = num<T>::zero();
-        state[5] = num<T>::zero();
-    } else {
-        const T err = fm::abs(res - state[2]);
-        state[2] = res;
-        state[3] = res;
-        state[4] = err;
-        if (err <= fm::err_target(res, rtol, atol) && may_stop(options, level, max_levels)) state[5] = num<T>::one();
-    }
+    level_step_apply<T, D>(low, up, tm, rtol, atol, level, nranks,
+                           [&](int r) {
+                               Comp<T> o;
+                               o.s = partials[2 * r];
+                               o.c = partials[2 * r + 1];
+                               return o;
+                           },
+                           state, options, max_levels);
 }
 
 }  // namespace fts

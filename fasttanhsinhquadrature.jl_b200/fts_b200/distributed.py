@@ -245,6 +245,14 @@ class ShardedPlan:
         L.check(L.lib.fts_peer_wait_ns(self.max_levels + 1, out))
         return np.array(out[: self.max_levels + 1], dtype=np.uint64)
 
+    def level_done_ns(self) -> np.ndarray:
+        """GPU globaltimer (ns) at which this rank finished the stop test of each level in the last fused call
+        (levels < 32); differences of neighbours are the per-level durations including the exchange"""
+        import ctypes as C
+        out = (C.c_uint64 * 64)()
+        L.check(L.lib.fts_peer_wait_ns(64, out))
+        return np.array(out[32: 32 + min(self.max_levels + 1, 32)], dtype=np.uint64)
+
 
 def adaptive_integrate_sharded(T, f, low, up, *, rtol=None, atol=0, max_levels: int = 5, cache=None, params=None, group=None,
                                warn: bool = True, shard_from_level: Optional[int] = None, exchange: str = "peer", force_depth: bool = False):

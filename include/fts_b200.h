@@ -350,8 +350,12 @@ int fts_adaptive_sharded_fused_opts_dev(fts_cache c, fts_integrand f, const void
 
 /* Per-level exchange wait of the LAST fts_adaptive_sharded_fused_dev call of this process: out[l] =
  * nanoseconds (%globaltimer) the device-side stop test of level l spent spinning on the slowest
- * peer's flag (0 for levels computed whole on every rank).  Synchronises the device.  The spin
- * gives up after FTS_B200_PEER_TIMEOUT_MS (environment, default 10000). */
+ * peer's flag (0 for levels computed whole on every rank), for l < 32; out[32 + l] = %globaltimer
+ * at the end of level l's stop test (neighbour differences = per-level durations, exchange
+ * included).  Synchronises the device.  The spin gives up after FTS_B200_PEER_TIMEOUT_MS
+ * (environment, default 10000).  By default the wait and the stop test run in the last CTA of the
+ * level kernel, and the levels that fit one CTA are walked in ONE launch; FTS_B200_STEP_FUSED=0
+ * selects the two-launch form (level kernel + one-warp stop-test kernel). */
 int fts_peer_wait_ns(int nlevels, uint64_t* out);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
