@@ -291,6 +291,10 @@ def sharded3d_record(fts, dev, world, rank, dist, levels, reps: int):
                     if world > 1:
                         dist.barrier()
                     torch.cuda.synchronize()
+                    # the ranks leave a host barrier tens of microseconds apart, which a 0.3 ms job would count as exchange
+                    # wait at its first sharded level: the streams are aligned by a device-side barrier (peer mailboxes)
+                    if world > 1 and arm != "single":
+                        fd.PeerMailboxes.get(None).barrier()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     plan.launch()

@@ -797,6 +797,35 @@ static int launch_cluster(const void* fn, unsigned nclusters, unsigned csize, in
     return FTS_OK;
 }
 
+// every CTA resident at once (the kernel has a grid-wide barrier): `grid` is cut to what the device can hold
+static int launch_cooperative(const void* fn, unsigned grid, int block, size_t smem, void* args, cudaStream_t s)
+{
+    if (int rc = ensure_dyn_smem(fn, smem)) return rc;
+    void* params[] = {args};
+    for (int per_sm = 4; per_sm >= 1; --per_sm) {
+        const unsigned cap = (unsigned)g_prop.multiProcessorCount * per_sm;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid < cap ? grid : cap);
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeCooperative;
+        attr.val.cooperative = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
+        if (e == cudaSuccess) {
+            g_launches.fetch_add(1);
+            return FTS_OK;
+        }
+        cudaGetLastError();
+        if (e != cudaErrorCooperativeLaunchTooLarge || per_sm == 1) return set_error(FTS_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
+    }
+    return FTS_OK;
+}
+
 // threads per CTA of the 1D thread-per-integral kernels: 128 (8 192 CTAs for 2^20 Float64
 // integrals: shorter tail than 256, 0.286 vs 0.290 ms on config B); Double64 prefers 256 (config E
 // 0.378 vs 0.394 ms); smaller CTAs for small batches were measured and do not help.
@@ -1100,6 +1129,33 @@ static int launch_level(const void* fn, fts_cache c, int dim, bool cmpl, const T
     return launch_raw(fn, grid_level_blocks(dim, level, nranks), fts::CTA_THREADS, grid_level_smem(dim, cmpl, level, sizeof(T)), &a, s);
 }
 
+// Levels lo ... hi of one integral in ONE launch of the level kernel (stop test in its last CTA).  More than one
+// CTA: cooperative launch + the generation barrier `gen`.  FTS_B200_GRID_RANGE = the deepest level that joins
+// the first launch (default 7: deeper levels last 100 us and more, they get a launch and a full-size grid each).
+static int range_top_level()
+{
+    static const int v = [] { const char* e = getenv("FTS_B200_GRID_RANGE"); const int x = e ? atoi(e) : 7; return x < 0 ? 0 : (x > 30 ? 30 : x); }();
+    return v;
+}
+template <class T>
+static int launch_level_range(const void* fn, fts::Args<T>& a, int dim, bool cmpl, int lo, int hi, unsigned int* gen, cudaStream_t s)
+{
+    unsigned blocks = 1;
+    for (int l = lo; l <= hi; ++l) {
+        const unsigned b = grid_level_blocks(dim, l, l >= a.shard_from ? a.nranks : 1);
+        if (b > blocks) blocks = b;
+        a.range_blocks[l & 31] = (unsigned short)b;
+    }
+    a.level = lo; a.level_hi = hi; a.step_fused = 1;
+    const size_t smem = grid_level_smem(dim, cmpl, hi, sizeof(T));
+    if (blocks == 1 || lo == hi) {
+        a.gen = nullptr;
+        return launch_raw(fn, blocks, fts::CTA_THREADS, smem, &a, s);
+    }
+    a.gen = gen;
+    return launch_cooperative(fn, blocks, fts::CTA_THREADS, smem, &a, s);
+}
+
 // FTS_B200_STEP_FUSED=0: the two-launch form (level kernel, then a one-warp stop-test kernel) for A/B runs
 static bool step_in_level_kernel()
 {
@@ -1125,12 +1181,13 @@ static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int o
     const bool cmpl = kind_cmpl(f->kind);
     const size_t nblk = (size_t)g_prop.multiProcessorCount * 4;
     T* scratch = nullptr;
-    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2 + 8 + 2) * sizeof(T), s));
+    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2 + 8 + 2) * sizeof(T) + 256, s));
     T* block_partials = scratch;
     T* partial = scratch + 2 * nblk;
     T* state = partial + 2;
-    unsigned int* ticket = (unsigned int*)(state + 8);
-    FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    unsigned int* ticket = (unsigned int*)(state + 8);  // ticket, and 128 B behind it (its own line: polled by every CTA) the generation barrier
+    unsigned int* gen = ticket + 32;
+    FTS_CUDA(cudaMemsetAsync(ticket, 0, 33 * sizeof(unsigned int), s));
     const T tm = load_elem<T>(c->tm);
     const bool one_launch = step_in_level_kernel();
     for (long long b = 0; b < batch; ++b) {
@@ -1138,20 +1195,19 @@ static int run_adaptive_grid(const void* fn, fts_cache c, fts_integrand f, int o
         const T* hi = up + b * bstride;
         const T* pp = params ? params + b * pstride : nullptr;
         for (int level = 0; level <= max_levels; ++level) {
-            if (one_launch) {  // stop test in the last CTA of the level kernel, one-CTA levels in one launch
+            if (one_launch) {  // stop test in the last CTA of the level kernel, levels 0 ... range_top_level() in one launch
                 fts::Args<T> a;
                 memset(&a, 0, sizeof a);
                 fill_cache_args(a, c);
                 a.low = lo; a.up = hi; a.params = pp; a.bstride = dim; a.pstride = 0; a.batch = 1;
-                a.level = level; a.rank = 0; a.nranks = 1;
+                a.rank = 0; a.nranks = 1;
                 a.block_partials = block_partials; a.ticket = ticket; a.partial_out = partial; a.state = level ? state : nullptr;
-                const unsigned blocks = grid_level_blocks(dim, level, 1);
                 int top = level;
-                if (blocks == 1)
-                    while (top < max_levels && grid_level_blocks(dim, top + 1, 1) == 1) ++top;
-                a.step_fused = 1; a.level_hi = top; a.state_out = state;
+                if (level == 0) top = max_levels < range_top_level() ? max_levels : range_top_level();
+                a.state_out = state;
+                a.gen_base = (unsigned int)b * 64u;
                 a.rtol = rtol; a.atol = atol; a.options = options; a.max_levels = max_levels;
-                if (int rc = launch_raw(fn, blocks, fts::CTA_THREADS, grid_level_smem(dim, cmpl, top, sizeof(T)), &a, s)) return rc;
+                if (int rc = launch_level_range<T>(fn, a, dim, cmpl, level, top, gen, s)) return rc;
                 level = top;
                 continue;
             }
@@ -1587,13 +1643,6 @@ extern "C" int fts_peer_free(void* dev_ptr)
     if (dev_ptr) FTS_CUDA(cudaFree(dev_ptr));
     return FTS_OK;
 }
-extern "C" int fts_peer_mailbox_bytes(int nranks, size_t* bytes)
-{
-    if (nranks < 1 || nranks > FTS_MAX_RANKS || !bytes) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad nranks");
-    *bytes = (size_t)2 * 64 * nranks * 4 * sizeof(double);  // [epoch parity][level < 64][rank]{s, c, flag, pad}
-    return FTS_OK;
-}
-
 // per-level exchange wait of the last fused call (ns, written by k_sharded_step_fused), and the
 // spin timeout of that kernel
 static unsigned long long peer_timeout_ns()
@@ -1604,6 +1653,49 @@ static unsigned long long peer_timeout_ns()
         return (unsigned long long)(ms < 1 ? 1 : ms) * 1000000ULL;
     }();
     return v;
+}
+
+extern "C" int fts_peer_mailbox_bytes(int nranks, size_t* bytes)
+{
+    if (nranks < 1 || nranks > FTS_MAX_RANKS || !bytes) return set_error(FTS_ERR_INVALID_ARGUMENT, "bad nranks");
+    *bytes = (size_t)(2 * 64 + 1) * nranks * 4 * sizeof(double);  // [epoch parity][level < 64][rank]{s, c, flag, pad}, then the row of fts_peer_barrier_dev
+    return FTS_OK;
+}
+
+// Device-side barrier of the ranks' streams through the mailboxes: lane r raises this rank's counter in rank r's
+// barrier row, then waits until every rank's counter in the own row has reached `count` (counts grow by one per
+// barrier of the group).  Aligns the streams to a few microseconds where a host barrier leaves tens.
+__global__ void k_peer_barrier(fts::PeerPtrs mail, int rank, int nranks, double count, unsigned long long timeout_ns, int* failed)
+{
+    const int lane = threadIdx.x;
+    if (lane < nranks) {
+        volatile double* theirs = mail.p[lane] + ((size_t)128 * nranks + rank) * 4;
+        theirs[2] = count;
+        __threadfence_system();
+        const volatile double* mine = mail.p[rank] + ((size_t)128 * nranks + lane) * 4;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (mine[2] < count) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                if (failed) *failed = 1;
+                break;
+            }
+        }
+    }
+}
+
+extern "C" int fts_peer_barrier_dev(void* const* mailboxes, int rank, int nranks, uint64_t count, void* stream)
+{
+    if (!mailboxes || nranks < 1 || nranks > FTS_MAX_RANKS || rank < 0 || rank >= nranks || count == 0)
+        return set_error(FTS_ERR_INVALID_ARGUMENT, "fts_peer_barrier_dev: mailboxes, 0 <= rank < nranks <= FTS_MAX_RANKS and a non-zero count");
+    if (int rc = ensure_init()) return rc;
+    fts::PeerPtrs m;
+    for (int r = 0; r < FTS_MAX_RANKS; ++r) m.p[r] = r < nranks ? (double*)mailboxes[r] : nullptr;
+    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(m, rank, nranks, (double)count, peer_timeout_ns(), nullptr);
+    g_launches.fetch_add(1);
+    FTS_CUDA(cudaGetLastError());
+    return FTS_OK;
 }
 
 extern "C" int fts_peer_wait_ns(int nlevels, uint64_t* out)
@@ -1624,10 +1716,11 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
     if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "no whole-grid level kernel for this integrand/dtype");
     const size_t nblk = (size_t)g_prop.multiProcessorCount * 4;
     T* scratch = nullptr;
-    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2 + 2) * sizeof(T), s));
+    FTS_CUDA(cudaMallocAsync((void**)&scratch, (2 * nblk + 2 + 2) * sizeof(T) + 256, s));
     T* partial = scratch + 2 * nblk;
-    unsigned int* ticket = (unsigned int*)(partial + 2);
-    FTS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    unsigned int* ticket = (unsigned int*)(partial + 2);  // ticket, and 128 B behind it (its own line: polled by every CTA) the generation barrier
+    unsigned int* gen = ticket + 32;
+    FTS_CUDA(cudaMemsetAsync(ticket, 0, 33 * sizeof(unsigned int), s));
     if (!g_peer_wait) {
         FTS_CUDA(cudaMalloc((void**)&g_peer_wait, 64 * sizeof(unsigned long long)));
         FTS_CUDA(cudaMemsetAsync(g_peer_wait, 0, 64 * sizeof(unsigned long long), s));
@@ -1651,15 +1744,20 @@ static int sharded_fused(fts_cache c, fts_integrand f, const T* low, const T* up
         }
         const unsigned blocks = grid_level_blocks(dim, level, a.nranks);
         if (one_launch) {
-            // exchange wait + stop test in the last CTA of the level kernel; the levels that fit one CTA (and
-            // agree on sharded / not sharded) are walked by that CTA in ONE launch
+            // exchange wait + stop test in the last CTA of the level kernel; levels 0 ... range_top_level() in ONE launch
             int hi = level;
-            if (blocks == 1)
-                while (hi < max_levels && grid_level_blocks(dim, hi + 1, a.nranks) == 1 && (mailboxes != nullptr && hi + 1 >= shard_from) == shard) ++hi;
-            a.step_fused = 1; a.level_hi = hi; a.state_out = state;
+            if (level == 0) hi = max_levels < range_top_level() ? max_levels : range_top_level();
+            a.rank = rank; a.nranks = mailboxes ? nranks : 1;
+            a.shard_from = mailboxes ? shard_from : 0;
+            if (mailboxes) {
+                for (int r = 0; r < nranks; ++r) a.peer_mail[r] = (double*)mailboxes[r];
+                a.mail_slot = parity * 64 + level;
+                a.epoch = epoch;
+            }
+            a.state_out = state;
             a.rtol = rtol; a.atol = atol; a.options = options; a.max_levels = max_levels;
             a.timeout_ns = tmo; a.wait_ns = g_peer_wait;
-            if (int rc = launch_raw(fn, blocks, fts::CTA_THREADS, grid_level_smem(dim, cmpl, hi, sizeof(T)), &a, s)) return rc;
+            if (int rc = launch_level_range<T>(fn, a, dim, cmpl, level, hi, gen, s)) return rc;
             level = hi;
             continue;
         }

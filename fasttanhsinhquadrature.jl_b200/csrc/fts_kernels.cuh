@@ -33,6 +33,8 @@ constexpr int TPI_PAIRS = FTS_TPI_PAIRS;  // node pairs per loop trip of the thr
 template <class T> struct Node { T x, w; };             // 1D / tensor tables, interleaved
 template <class T> struct NodeC { T x, w, c, pad; };    // complement tables
 
+struct PeerPtrs { double* p[FTS_MAX_RANKS]; };  // the ranks' mailboxes as a kernel argument
+
 template <class T> struct Args {
     // fixed grid (x,w,h) = tanhsinh(T,N)
     const Node<T>* grid;
@@ -93,6 +95,10 @@ template <class T> struct Args {
     // levels level ... level_hi in one launch (the levels that are one CTA small)
     int step_fused;
     int level_hi;
+    int shard_from;                    // levels of the range below this one: whole on every rank, no exchange
+    unsigned int* gen;                 // generation barrier of a multi-CTA range (cooperative launch); null: one CTA or one level
+    unsigned short range_blocks[32];   // CTAs that work on level l of a multi-CTA range (<= gridDim.x)
+    unsigned int gen_base;             // the barrier counts gen_base + level + 1 (one zeroed word serves the integrals of a call one after the other)
     T* state_out;
     unsigned long long timeout_ns;     // peer wait limit
     unsigned long long* wait_ns;       // [64] or null: [level] exchange wait, [32 + level] globaltimer when the level's stop test was done

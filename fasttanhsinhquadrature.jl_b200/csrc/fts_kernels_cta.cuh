@@ -1020,28 +1020,78 @@ __device__ __forceinline__ bool peer_wait_flags(const double* mail, int slot_row
 // Partial sum of level `a.level` (0 = base grid) of ONE 2D/3D integral (bounds/params at index
 // 0), flat new-cell index dealt over gridDim.x CTAs and a.nranks devices.  The last CTA to
 // finish (ticket) merges the per-CTA (s,c) partials in CTA order and writes a.partial_out[0..1].
+//
+// a.step_fused: that last CTA also exchanges the partial with the peers (mailboxes over NVLink), waits for
+// theirs and does the stop test of the level, and the kernel walks the levels a.level ... a.level_hi in ONE
+// launch.  With more than one CTA (a.gen != nullptr; cooperative launch, every CTA resident) the other CTAs
+// wait at a generation barrier for the last CTA's verdict: one launch per integral for the levels whose
+// duration is of the order of a launch (levels 0 ... 7 of a 3D integral: 6-10 us each as launches, 2-3 us
+// as barrier rounds), which is what bounds the strong scaling of a sharded integral.  Levels below
+// a.shard_from are computed whole on every rank (no exchange), the others on this rank's shard.
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+// the generation word holds (count << 1) | done; counts are compared modulo 2^31
+__device__ __forceinline__ unsigned int wait_generation(const unsigned int* gen, unsigned int target)
+{
+    unsigned int v;
+    for (;;) {
+        v = ld_acquire_gpu(gen);
+        if ((int)(((v >> 1) - target) << 1) >= 0) break;
+        __nanosleep(40);  // several hundred CTAs poll one word: leave the L2 slice room for the store they wait for
+    }
+    return v;
+}
+
 template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS) k_level_grid(const Args<T> a)
 {
     constexpr bool CMPL = is_cmpl2d<F>::value;
     __shared__ T red[64];
     __shared__ int s_last;
+    __shared__ unsigned int s_gen;
     if (a.state && a.state[5] != num<T>::zero()) return;  // converged at an earlier level
     family_tables_init<T, F>();
     const int tid = threadIdx.x;
     T p[F::NP > 0 ? F::NP : 1];
     load_params<F::NP>(p, a, 0);
     const T half = num<T>::half();
-    const long long gthreads = (long long)gridDim.x * blockDim.x;
-    const long long start = (long long)a.rank * gthreads + (long long)blockIdx.x * blockDim.x + tid;
-    const long long stride = gthreads * a.nranks;
     const int level_hi = a.step_fused ? a.level_hi : a.level;
     for (int level = a.level; level <= level_hi; ++level) {
-        if (a.step_fused && level > 0) {  // converged at an earlier level (this call: state_out is only written by last CTAs)
-            if (__ldcg(a.state_out + 5) != num<T>::zero()) {
+        if (a.step_fused && level > a.level) {  // converged at an earlier level of this launch (state_out is only written by last CTAs)
+            const bool done = a.gen ? (s_gen & 1u) != 0u : __ldcg(a.state_out + 5) != num<T>::zero();
+            if (done) {
                 if (a.wait_ns && blockIdx.x == 0 && tid == 0) a.wait_ns[level] = 0ULL;
                 return;
             }
         }
+        const bool sharded = level >= a.shard_from;
+        const int rank = sharded ? a.rank : 0, nranks = sharded ? a.nranks : 1;
+        // CTAs of the level: the whole grid, or the first range_blocks[level] CTAs of a multi-CTA range (a small level on
+        // 592 CTAs would spend its time in 592 tickets to one address and a 592-term merge)
+        const unsigned int nblk = a.gen ? min((unsigned int)a.range_blocks[level & 31], gridDim.x) : gridDim.x;
+        if (blockIdx.x >= nblk) {
+            if (level == level_hi) return;
+            if (tid == 0) s_gen = wait_generation(a.gen, a.gen_base + (unsigned int)(level + 1));
+            __syncthreads();
+            continue;
+        }
+        const long long gthreads = (long long)nblk * blockDim.x;
+        const long long start = (long long)rank * gthreads + (long long)blockIdx.x * blockDim.x + tid;
+        const long long stride = gthreads * nranks;
         const int n = level == 0 ? 2 : (2 << level);
         T acc;
         if constexpr (D == 3) {
@@ -1078,15 +1128,19 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
         if (tid == 0) {
             a.block_partials[2 * blockIdx.x] = bsum.s;
             a.block_partials[2 * blockIdx.x + 1] = bsum.c;
-            __threadfence();
-            const unsigned int t = atomicAdd(a.ticket, 1u);
-            s_last = (t == gridDim.x - 1) ? 1 : 0;
+            const unsigned int t = atom_add_acq_rel_gpu(a.ticket, 1u);  // releases the partials, acquires the other CTAs'
+            s_last = (t == nblk - 1) ? 1 : 0;
         }
         __syncthreads();
-        if (!s_last) return;
-        __threadfence();
+        if (!s_last) {
+            if (!a.step_fused || level == level_hi || a.gen == nullptr) return;
+            // generation barrier: the last CTA publishes level + 1 (and the verdict) after the stop test of the level
+            if (tid == 0) s_gen = wait_generation(a.gen, a.gen_base + (unsigned int)(level + 1));
+            __syncthreads();
+            continue;
+        }
         Comp<T> tot;
-        for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+        for (int i = tid; i < (int)nblk; i += blockDim.x) {
             Comp<T> o;
             o.s = __ldcg(a.block_partials + 2 * i);
             o.c = __ldcg(a.block_partials + 2 * i + 1);
@@ -1098,14 +1152,14 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
             a.partial_out[1] = tot.c;
             *a.ticket = 0u;
         }
-        const bool exchange = a.peer_mail[0] != nullptr;
+        const bool exchange = a.peer_mail[0] != nullptr && sharded;
         const int slot_row = a.mail_slot + (level - a.level);
         // fused all-gather: one lane per destination rank writes {s, c} into that rank's mailbox over
         // NVLink (or locally for r == rank), fences system-wide, then raises the epoch flag
-        if (exchange && tid < a.nranks) {
-            const double s_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.s, 0));
-            const double c_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - a.nranks), tot.c, 0));
-            volatile double* slot = a.peer_mail[tid] + ((size_t)slot_row * a.nranks + a.rank) * 4;
+        if (exchange && tid < nranks) {
+            const double s_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - nranks), tot.s, 0));
+            const double c_ = num<T>::to_double(__shfl_sync(0xffffffffu >> (32 - nranks), tot.c, 0));
+            volatile double* slot = a.peer_mail[tid] + ((size_t)slot_row * nranks + rank) * 4;
             slot[0] = s_;
             slot[1] = c_;
             __threadfence_system();
@@ -1117,13 +1171,13 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
             bool ok = true;
             unsigned long long waited = 0ULL;
             const double* mail = a.peer_mail[a.rank];
-            if (exchange) ok = peer_wait_flags(mail, slot_row, a.nranks, a.epoch, a.timeout_ns, &waited);
+            if (exchange) ok = peer_wait_flags(mail, slot_row, nranks, a.epoch, a.timeout_ns, &waited);
             if (tid == 0) {
                 if (!ok) a.state_out[5] = num<T>::from_double(3.0);
                 else if (exchange)
-                    level_step_apply<T, D>(a.low, a.up, a.tm, a.rtol, a.atol, level, a.nranks,
+                    level_step_apply<T, D>(a.low, a.up, a.tm, a.rtol, a.atol, level, nranks,
                                            [&](int r) {
-                                               const volatile double* slot = mail + ((size_t)slot_row * a.nranks + r) * 4;
+                                               const volatile double* slot = mail + ((size_t)slot_row * nranks + r) * 4;
                                                Comp<T> o;
                                                o.s = num<T>::from_double(slot[0]);
                                                o.c = num<T>::from_double(slot[1]);
@@ -1138,10 +1192,15 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
                     a.wait_ns[level] = waited;
                     if (level < 32) a.wait_ns[32 + level] = now;
                 }
-                __threadfence();
+                if (a.gen) {
+                    s_gen = ((a.gen_base + (unsigned int)(level + 1)) << 1) | (a.state_out[5] != num<T>::zero() ? 1u : 0u);
+                    st_release_gpu(a.gen, s_gen);
+                } else {
+                    __threadfence();
+                }
             }
         }
-        __syncthreads();  // a range of levels is walked by ONE CTA: the next level re-stages shared memory and reads the state
+        __syncthreads();  // the next level re-stages shared memory and reads the state
     }
 }
 

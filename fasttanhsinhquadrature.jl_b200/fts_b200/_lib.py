@@ -99,6 +99,7 @@ _SIGS = {
     "fts_peer_free": (ci, [vp]),
     "fts_adaptive_sharded_fused_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp), C.c_uint64, vp, vp]),
     "fts_peer_wait_ns": (ci, [ci, C.POINTER(C.c_uint64)]),
+    "fts_peer_barrier_dev": (ci, [C.POINTER(vp), ci, ci, C.c_uint64, vp]),
     "fts_adaptive_sharded_fused_opts_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp), C.c_uint64, vp, ci, vp]),
     "fts_integrand_cubin_size": (ci, [vp, C.POINTER(cs_), C.POINTER(ci)]),
     "fts_measure_fma_peak": (ci, [ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

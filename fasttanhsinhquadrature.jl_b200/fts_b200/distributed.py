@@ -143,6 +143,16 @@ class PeerMailboxes:
                 self.opened.append(ptr)
             dist.barrier(group=group)
         self.epoch = 0
+        self.barriers = 0
+
+    def barrier(self, stream=None) -> None:
+        """queue a device-side barrier of the ranks' streams (fts_peer_barrier_dev); every rank must call it"""
+        import ctypes as C
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        self.barriers += 1
+        L.check(L.lib.fts_peer_barrier_dev(self.ptrs, self.rank, self.world, C.c_uint64(self.barriers), C.c_void_p(stream)))
 
     @classmethod
     def get(cls, group=None) -> "PeerMailboxes":

@@ -348,6 +348,11 @@ int fts_adaptive_sharded_fused_opts_dev(fts_cache c, fts_integrand f, const void
                                         void* const* mailboxes, uint64_t epoch, void* state_dev,
                                         int options, void* stream);
 
+/* Device-side barrier of the ranks' streams through the mailboxes (kernel on `stream`, no host
+ * synchronisation): returns at once; work queued behind it starts within microseconds of the same
+ * moment on every rank.  `count` = 1, 2, 3 ... per barrier of the group, the same on every rank. */
+int fts_peer_barrier_dev(void* const* mailboxes, int rank, int nranks, uint64_t count, void* stream);
+
 /* Per-level exchange wait of the LAST fts_adaptive_sharded_fused_dev call of this process: out[l] =
  * nanoseconds (%globaltimer) the device-side stop test of level l spent spinning on the slowest
  * peer's flag (0 for levels computed whole on every rank), for l < 32; out[32 + l] = %globaltimer
