@@ -81,10 +81,13 @@ FTS_HD dd operator/(dd a, dd b)
 {
     double q1 = a.hi / b.hi;
     if (!dd_finite(q1) || !dd_finite(b.hi)) return dd(q1);
+    // the later quotient digits come off one reciprocal (a double division is ~25 instructions on the GPU;
+    // the digits only have to be good to a few ulps, each remainder corrects the one before)
+    const double rcp = 1.0 / b.hi;
     dd r = a - b * q1;
-    double q2 = r.hi / b.hi;
+    double q2 = r.hi * rcp;
     r = r - b * q2;
-    double q3 = r.hi / b.hi;
+    double q3 = r.hi * rcp;
     dd q = quick_two_sum(q1, q2);
     return q + q3;
 }
@@ -112,55 +115,152 @@ FTS_HD dd dd_sqrt(dd a)
     return quick_two_sum(ax, 0.0) + r.hi * (x * 0.5);
 }
 
-// exp(dd): k = round(x/ln2), r = (x - k ln2)/512, Taylor on r, square 9 times, scale by 2^k.
+// 1/sqrt(a): double estimate y, then one Newton step in double-double, y + y (1 - a y^2)/2 (error 1.5 delta^2 of the
+// estimate's delta ~ 1e-16); ~45 FP64 instructions where 1/dd_sqrt(a) spends three divisions and a square root
+FTS_HD dd dd_rsqrt(dd a)
+{
+    if (a.hi <= 0.0) return dd(a.hi == 0.0 ? dd_inf() : dd_nan());
+    if (!dd_finite(a.hi)) return dd(a.hi != a.hi ? a.hi : 0.0);
+    // subnormal and near-overflow arguments: scale by an even power of two (exact)
+    double sc = 1.0;
+    if (a.hi < 0x1p-900) { a = dd_mul_pwr2(a, 0x1p200); sc = 0x1p100; }
+    else if (a.hi > 0x1p900) { a = dd_mul_pwr2(a, 0x1p-200); sc = 0x1p-100; }
+#ifdef __CUDA_ARCH__
+    const double y = ::rsqrt(a.hi);
+#else
+    const double y = 1.0 / ::sqrt(a.hi);
+#endif
+    const dd t = a * two_prod(y, y);
+    const double e = (1.0 - t.hi) - t.lo;
+    const dd r = quick_two_sum(y, (0.5 * y) * e);
+    return sc == 1.0 ? r : dd_mul_pwr2(r, sc);
+}
+
+// ---- exp / log: table-driven (tools/gen_dd_tables.py), ~180 / ~160 FP64 instructions per call ----------------
+// (the QD-style forms they replace — Taylor + nine squarings, two Newton steps on that exp — cost ~700 / ~1500)
+#include "fts_dd_tables.inc"
+static const double dd_exp2_tab_host[64][2] = FTS_DD_EXP2_TAB_VALUES;
+static const double dd_log_tab_host[97][2] = FTS_DD_LOG_TAB_VALUES;
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+static __device__ const double dd_exp2_tab_dev[64][2] = FTS_DD_EXP2_TAB_VALUES;
+static __device__ const double dd_log_tab_dev[97][2] = FTS_DD_LOG_TAB_VALUES;
+#endif
+FTS_HD dd dd_exp2_tab(int j)
+{
+#ifdef __CUDA_ARCH__
+    const double2 v = __ldg(reinterpret_cast<const double2*>(&dd_exp2_tab_dev[j][0]));
+    return dd(v.x, v.y);
+#else
+    return dd(dd_exp2_tab_host[j][0], dd_exp2_tab_host[j][1]);
+#endif
+}
+FTS_HD dd dd_log_tab(int j)
+{
+#ifdef __CUDA_ARCH__
+    const double2 v = __ldg(reinterpret_cast<const double2*>(&dd_log_tab_dev[j][0]));
+    return dd(v.x, v.y);
+#else
+    return dd(dd_log_tab_host[j][0], dd_log_tab_host[j][1]);
+#endif
+}
+
+// a + b for |a.hi| >= |b.hi| (or a.hi == 0): 8 flops instead of 20
+FTS_HD dd dd_add_big(dd a, dd b)
+{
+    dd s = quick_two_sum(a.hi, b.hi);
+    s.lo += a.lo + b.lo;
+    return quick_two_sum(s.hi, s.lo);
+}
+
+// exp(dd): x = n ln2/64 + r, |r| <= ln2/128; exp(r) = 1 + r + r^2 p(r) with the terms r^2/2! ... r^6/6! in
+// double-double and r^7/7! ... r^13/13! in double; exp(x) = 2^(n >> 6) * 2^((n & 63)/64) * exp(r).
 FTS_HD dd dd_exp(dd a)
 {
-    const dd LN2(6.931471805599452862e-01, 2.319046813846299558e-17);
+    // ln2/64 = H + M: H carries 30 bits, so n H is exact for |n| < 2^23 and the reduction loses nothing at |x| ~ 700
+    const double LN2_64_H = 0x1.62e42fe800000p-7;
+    const dd LN2_64_M(0x1.e8e7bcd5e4f1ep-37, -0x1.8cff81a12a17ep-91);
     if (a.hi != a.hi) return dd(a.hi);
     if (a.hi < -745.2) return dd(0.0);  // down to the smallest subnormal (ldexp below rounds once)
     if (a.hi >= 709.0) return dd(dd_inf());
     if (a.hi == 0.0 && a.lo == 0.0) return dd(1.0);
-    double kf = ::floor(a.hi / LN2.hi + 0.5);
-    dd r = dd_mul_pwr2(a - LN2 * kf, 1.0 / 512.0);
-    // Taylor series sum_{i>=1} r^i/i!  (|r| <= ln2/1024: 9 terms reach 2^-110)
-    const dd inv_fact[8] = {dd(1.66666666666666657e-01, 9.25185853854297066e-18), dd(4.16666666666666644e-02, 2.31296463463574266e-18),
-                            dd(8.33333333333333322e-03, 1.15648231731787138e-19), dd(1.38888888888888894e-03, -5.30054395437357706e-20),
-                            dd(1.98412698412698413e-04, 1.72095582934207053e-22), dd(2.48015873015873016e-05, 2.15119478667758816e-23),
-                            dd(2.75573192239858925e-06, -1.85839327404647208e-22), dd(2.75573192239858883e-07, 2.37677146222502973e-23)};
-    dd p = r * r;
-    dd s = r + dd_mul_pwr2(p, 0.5);
-    p = p * r;
-    dd t = p * inv_fact[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-        s = s + t;
-        p = p * r;
-        t = p * inv_fact[i];
-    }
-    s = s + t;
-    // (1+s)^512 - 1 by nine doublings: s <- 2s + s^2
-#pragma unroll
-    for (int i = 0; i < 9; ++i) s = dd_mul_pwr2(s, 2.0) + s * s;
-    s = s + 1.0;
-    return dd_ldexp(s, (int)kf);
+    const double nf = ::floor(a.hi * 0x1.71547652b82fep+6 + 0.5);
+    const dd r = (a + (-(LN2_64_H * nf))) - LN2_64_M * nf;
+    const int n = (int)nf;
+    const double rh = r.hi;
+    double q = 0x1.6124613a86d09p-33;
+    q = ::fma(q, rh, 0x1.1eed8eff8d898p-29);
+    q = ::fma(q, rh, 0x1.ae64567f544e4p-26);
+    q = ::fma(q, rh, 0x1.27e4fb7789f5cp-22);
+    q = ::fma(q, rh, 0x1.71de3a556c734p-19);
+    q = ::fma(q, rh, 0x1.a01a01a01a01ap-16);
+    q = ::fma(q, rh, 0x1.a01a01a01a01ap-13);
+    dd p = dd_add_big(dd(0x1.6c16c16c16c17p-10, -0x1.f49f49f49f49fp-65), r * q);
+    p = dd_add_big(dd(0x1.1111111111111p-7, 0x1.1111111111111p-63), p * r);
+    p = dd_add_big(dd(0x1.5555555555555p-5, 0x1.5555555555555p-59), p * r);
+    p = dd_add_big(dd(0x1.5555555555555p-3, 0x1.5555555555555p-57), p * r);
+    p = dd_add_big(dd(0.5), p * r);
+    const dd s = dd_add_big(r, (r * r) * p);
+    const dd e = dd_add_big(dd(1.0), s) * dd_exp2_tab(n & 63);
+    return dd_ldexp(e, n >> 6);
 }
 
-// log(dd): one Newton step on exp from the double estimate: x1 = x0 + a*exp(-x0) - 1
+// 1/d to ~2^-50 for d in [1, 4) (the quotient digits of dd_log's division need no more)
+FTS_HD double dd_rcp_approx(double d)
+{
+#ifdef __CUDA_ARCH__
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = ::fma(-d, x, 1.0);
+    x = ::fma(x, e, x);
+    e = ::fma(-d, x, 1.0);
+    return ::fma(x, e, x);
+#else
+    return 1.0 / d;
+#endif
+}
+
+// log(dd): a = m 2^e with m in [0.75, 1.5); c = the nearest of the 97 points 0.75 + j/128 (c = 1 for m near 1, so
+// that log keeps its relative accuracy there); s = (m - c)/(m + c), |s| < 1/383;
+// log m = log c + 2 atanh(s) = log c + 2 (s + s^3/3 + s^5/5 + ... + s^15/15), the terms from s^7 on in double.
 FTS_HD dd dd_log(dd a)
 {
     if (a.hi <= 0.0)
         return dd(a.hi == 0.0 ? (-dd_inf()) : dd_nan());
     if (a.hi - a.hi != 0.0) return a;  // +Inf
-    // a = m * 2^e with m in [0.5, 1): Newton on m keeps exp(-x) of order one for every finite a
-    // (subnormal complement distances down to 1e-310 included), then log a = log m + e ln2
     const dd LN2(6.931471805599452862e-01, 2.319046813846299558e-17);
     int e = 0;
-    const double mh = ::frexp(a.hi, &e);
-    const dd m(mh, ::ldexp(a.lo, -e));
-    dd x(::log(mh));
-    x = x + (m * dd_exp(-x) - dd(1.0));
-    x = x + (m * dd_exp(-x) - dd(1.0));
-    return x + LN2 * (double)e;
+    double mh = ::frexp(a.hi, &e);     // [0.5, 1); subnormal complement distances down to 1e-310 included
+    if (mh < 0.75) {
+        mh *= 2.0;
+        e -= 1;
+    }
+    const double ml = ::ldexp(a.lo, -e);
+    const int j = (int)::floor((mh - 0.75) * 128.0 + 0.5);
+    const double c = 0.75 + (double)j * 0.0078125;
+    const dd num = two_sum(mh - c, ml);          // mh - c is exact (Sterbenz)
+    dd den = two_sum(mh, c);
+    den.lo += ml;
+    den = quick_two_sum(den.hi, den.lo);
+    // s = num / den, three quotient digits off one approximate reciprocal
+    const double rcp = dd_rcp_approx(den.hi);
+    const double q1 = num.hi * rcp;
+    dd rem = num - den * q1;
+    const double q2 = rem.hi * rcp;
+    rem = rem - den * q2;
+    const double q3 = rem.hi * rcp;
+    const dd s = dd_add_big(quick_two_sum(q1, q2), dd(q3));
+    const dd t = s * s;
+    const double th = t.hi;
+    double q = 0x1.1111111111111p-4;
+    q = ::fma(q, th, 0x1.3b13b13b13b14p-4);
+    q = ::fma(q, th, 0x1.745d1745d1746p-4);
+    q = ::fma(q, th, 0x1.c71c71c71c71cp-4);
+    q = ::fma(q, th, 0x1.2492492492492p-3);
+    dd u = dd_add_big(dd(0x1.999999999999ap-3, -0x1.999999999999ap-57), dd(th * q));
+    u = dd_add_big(dd(0x1.5555555555555p-2, 0x1.5555555555555p-56), t * u);
+    const dd lg = dd_mul_pwr2(dd_add_big(s, s * (t * u)), 2.0);
+    if (e == 0) return j == 32 ? lg : dd_log_tab(j) + lg;
+    return (LN2 * (double)e + dd_log_tab(j)) + lg;
 }
 
 // sin/cos(dd): k = round(x/(pi/2)), r = x - k pi/2 (|r| <= pi/4), Taylor for sin(r/8),

@@ -142,13 +142,21 @@ struct F1Poly6 {  // x^6 - 2x^3 + 0.5   benchmarks.jl:33
 };
 struct F1InvSqrtAbs {  // c/sqrt(|x|)   test/runtests.jl:74
     static constexpr int NP = 1;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p) { return p[0] / fm::sqrt(fm::abs(x)); }
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T x, const T* p)
+    {
+        if constexpr (sizeof(T) == 16) return p[0] * dd_rsqrt(fm::abs(x));  // Double64: no reference bits to keep, 5x fewer instructions
+        else return p[0] / fm::sqrt(fm::abs(x));
+    }
 };
 
 // ---------------------------------------------------------------- 1D complement: f(x,bmx,xma)
 struct C1InvSqrt {  // c/sqrt(bmx*xma)   test/runtests.jl:82, families_1d.jl:10
     static constexpr int NP = 1;
-    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T xma, const T* p) { return p[0] / fm::sqrt(bmx * xma); }
+    template <class T, bool FAST> static __device__ __forceinline__ T eval(T, T bmx, T xma, const T* p)
+    {
+        if constexpr (sizeof(T) == 16) return p[0] * dd_rsqrt(bmx * xma);  // Double64: no reference bits to keep, 5x fewer instructions
+        else return p[0] / fm::sqrt(bmx * xma);
+    }
 };
 struct C1LogBmx {
     static constexpr int NP = 0;

@@ -1431,7 +1431,22 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
             }
         }
     }
-    if (int rc = launch(fn, batch, tpi_block(dim, c->dtype), &a, s)) return rc;
+    // Double64, 1D: a group of 4 (FTS_B200_DD_GROUP = 2: 2, 1: off) lanes per integral while that still leaves the
+    // GPU under a few waves (k_adaptive1d_grp)
+    long long threads = batch;
+    if (is_dd && dim == 1) {
+        static const int dd_group = [] { const char* e = getenv("FTS_B200_DD_GROUP"); const int v = e ? atoi(e) : 4; return v == 2 || v == 4 ? v : 1; }();
+        if (dd_group > 1 && batch * dd_group <= (1LL << 21)) {
+            const void* fn_grp = integrand_kernel(f, c->dtype, KID_ADAPT_GRP, dd_group == 2 ? 1 : 0);
+            if (fn_grp) {
+                fn = fn_grp;
+                threads = batch * dd_group;
+            } else {
+                g_last_error.clear();
+            }
+        }
+    }
+    if (int rc = launch(fn, threads, tpi_block(dim, c->dtype), &a, s)) return rc;
     if (fn_bucket) {
         const int* ctl = a.sort_ctl;
         int* base = a.sort_idx;

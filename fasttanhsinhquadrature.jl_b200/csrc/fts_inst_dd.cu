@@ -6,15 +6,19 @@
         {FAM, FTS_DD64, fts_host::KID_FIXED_TPI, 0, FTS_KPTR(fts::k_fixed1d_tpi<fts::dd, fts::FUNCTOR, false>)},   \
         {FAM, FTS_DD64, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::k_adaptive1d_tpi<fts::dd, fts::FUNCTOR, false>)}, \
         {FAM, FTS_DD64, fts_host::KID_ADAPT_TAIL, 0, FTS_KPTR(fts::k_adaptive1d_tail<fts::dd, fts::FUNCTOR, false, false>)}, \
+        {FAM, FTS_DD64, fts_host::KID_ADAPT_GRP, 0, FTS_KPTR(fts::k_adaptive1d_grp<fts::dd, fts::FUNCTOR, false, 4>)}, \
+        {FAM, FTS_DD64, fts_host::KID_ADAPT_GRP, 1, FTS_KPTR(fts::k_adaptive1d_grp<fts::dd, fts::FUNCTOR, false, 2>)}, \
     };                                                                                                       \
-    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 3);
+    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 5);
 
 #define FTS_REGISTER_DD_C1(FAM, FUNCTOR)                                                                     \
     static const fts_host::KernelEntry k_dd_entries_##FUNCTOR[] = {                                         \
         {FAM, FTS_DD64, fts_host::KID_ADAPT_TPI, 0, FTS_KPTR(fts::k_adaptive1d_cmpl_tpi<fts::dd, fts::FUNCTOR, false>)}, \
         {FAM, FTS_DD64, fts_host::KID_ADAPT_TAIL, 0, FTS_KPTR(fts::k_adaptive1d_tail<fts::dd, fts::FUNCTOR, false, true>)}, \
+        {FAM, FTS_DD64, fts_host::KID_ADAPT_GRP, 0, FTS_KPTR(fts::k_adaptive1d_grp<fts::dd, fts::FUNCTOR, true, 4>)}, \
+        {FAM, FTS_DD64, fts_host::KID_ADAPT_GRP, 1, FTS_KPTR(fts::k_adaptive1d_grp<fts::dd, fts::FUNCTOR, true, 2>)}, \
     };                                                                                                       \
-    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 2);
+    static fts_host::Registrar k_dd_reg_##FUNCTOR(k_dd_entries_##FUNCTOR, 4);
 
 FTS_REGISTER_DD_1D(FTS_F1_POLY7, F1Poly7)
 FTS_REGISTER_DD_1D(FTS_F1_EXP, F1Exp)

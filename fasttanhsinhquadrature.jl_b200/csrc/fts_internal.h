@@ -24,7 +24,8 @@ enum KernelId : int {
     KID_FIXED_CMPL = 9,    // k_fixed1d_cmpl_tpi              integrate1D_cmpl (fixed grid, complement signature)
     KID_ADAPT_WARP = 10,   // k_adaptive2d_warp               warp per integral, shallow levels (large 2D batches, FAST only)
     KID_ADAPT_BUCKET = 11, // k_adaptive1d_bucket             warp tasks over bound-ordered chunks (1D exp families, Float64, arbitrary parameter order)
-    KID_COUNT = 12
+    KID_ADAPT_GRP = 12,    // k_adaptive1d_grp                a group of 4 lanes per integral (Double64, 1D kinds); `fast` = 1: groups of 2
+    KID_COUNT = 13
 };
 
 struct KernelEntry {

@@ -606,6 +606,130 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256) k_
     store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
 }
 
+// ---- a group of G lanes per integral (Double64, 1D) -------------------------------------------------------
+// A Double64 evaluation is 100-300 FP64 instructions of mostly dependent arithmetic, and BASELINE config E
+// (65 536 integrals) is 3.5 warps per scheduler with one thread per integral: the FP64 pipe idles two thirds
+// of the time.  Here G neighbouring lanes share an integral: lane g takes the nodes g, g + G, ... of a level,
+// sums them in index order, and the G partial sums are added in lane order (a fixed tree of shuffles), so the
+// result depends on G but not on the batch or the launch.  Nothing pins the summation order of Double64
+// (the reference holds no Double64 value; tolerance 1e-28 against a 1e-32 format).  Integrals still
+// unconverged at Args::tail_level join the deep queue like those of the thread-per-integral kernels.
+template <class T> __device__ __forceinline__ T shfl_xor_t(unsigned mask, T v, int lane_mask)
+{
+    if constexpr (sizeof(T) == 16) {
+        T r;
+        r.hi = __shfl_xor_sync(mask, v.hi, lane_mask);
+        r.lo = __shfl_xor_sync(mask, v.lo, lane_mask);
+        return r;
+    } else {
+        return __shfl_xor_sync(mask, v, lane_mask);
+    }
+}
+template <class T> __device__ __forceinline__ T shfl_t(unsigned mask, T v, int src)
+{
+    if constexpr (sizeof(T) == 16) {
+        T r;
+        r.hi = __shfl_sync(mask, v.hi, src);
+        r.lo = __shfl_sync(mask, v.lo, src);
+        return r;
+    } else {
+        return __shfl_sync(mask, v, src);
+    }
+}
+// sum over the lanes of a group, the same bits on every lane (the group's first lane's value is broadcast)
+template <class T, int G> __device__ __forceinline__ T group_sum(unsigned mask, T v, int first_lane)
+{
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) v = v + shfl_xor_t<T>(mask, v, m);
+    return shfl_t<T>(mask, v, first_lane);
+}
+
+template <class T, class F, bool CMPL, int G> __global__ void __launch_bounds__(256) k_adaptive1d_grp(const Args<T> a)
+{
+    static_assert(G == 2 || G == 4 || G == 8, "group sizes");
+    pdl_launch_dependents();
+    family_tables_init<T, F>();
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long b = gt / G;
+    if (b >= a.batch) return;  // whole groups leave together (blockDim.x is a multiple of G)
+    const int lane = threadIdx.x & 31, g = lane & (G - 1), first = lane - g;
+    const unsigned mask = ((1u << G) - 1u) << first;
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half(), one = num<T>::one();
+    T lo = a.low[b * a.bstride], hi = a.up[b * a.bstride];
+    bool neg = false;
+    int flags = 0;
+    if (a.options & OPT_QUAD_EDGE) {
+        if (!quad_edge_axis(lo, hi, neg)) {
+            if (g == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+            return;
+        }
+        if (neg) flags |= FLAG_FLIPPED;
+    }
+    const T dx = half * (hi - lo), x0 = half * (hi + lo);
+    auto pair = [&](T xk, T ck, T wk) -> T {
+        const T d = dx * xk;
+        if constexpr (CMPL) {
+            const T dxck = dx * ck, dx1p = dx * (one + xk);
+            return wk * (F::template eval<T, false>(d + x0, dxck, dx1p, p) + F::template eval<T, false>(x0 - d, dx1p, dxck, p));
+        } else {
+            return wk * (F::template eval<T, false>(d + x0, p) + F::template eval<T, false>(x0 - d, p));
+        }
+    };
+    T h = a.tm * half;
+    // base grid: centre, pair 0, pair 1 on lanes 0, 1, 2
+    T part = num<T>::zero();
+    if (g == 0) {
+        if constexpr (CMPL) part = num<T>::half_pi() * F::template eval<T, false>(x0, dx, dx, p);
+        else part = num<T>::half_pi() * F::template eval<T, false>(x0, p);
+    }
+    if constexpr (G >= 4) {
+        if (g == 1 || g == 2) part = pair(a.ix[g - 1], a.ic[g - 1], a.iw[g - 1]);
+    } else {
+        if (g == 1) part = pair(a.ix[0], a.ic[0], a.iw[0]);
+        else part = part + pair(a.ix[1], a.ic[1], a.iw[1]);
+    }
+    T s_total = group_sum<T, G>(mask, part, first);
+    T old_res = dx * h * s_total;
+    T err = num<T>::zero();
+    int level_used = 0;
+    for (int level = 1; level <= a.max_levels; ++level) {
+        h = h * half;
+        const int n = 1 << level;
+        part = num<T>::zero();
+        for (int i = g; i < n; i += G) {
+            if constexpr (CMPL) {
+                const NodeC<T> nd = a.nodes_c[(n - 2) + i];
+                part = part + pair(nd.x, nd.c, nd.w);
+            } else {
+                const Node<T> nd = ldg_node(a.nodes + (n - 2) + i);
+                part = part + pair(nd.x, nd.x, nd.w);
+            }
+        }
+        s_total = s_total + group_sum<T, G>(mask, part, first);
+        const T new_res = dx * h * s_total;
+        err = fm::abs(new_res - old_res);
+        level_used = level;
+        old_res = new_res;
+        if (err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels)) {
+            flags |= FLAG_CONVERGED;
+            break;
+        }
+        if (level == a.tail_level && level < a.max_levels) {  // park and let a whole CTA finish it
+            if (g == 0) {
+                a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
+                a.value[b] = s_total;
+            }
+            return;
+        }
+    }
+    if (g == 0) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
 // s += terms[0] + terms[1] + ... in index order, one thread.  The chain of dependent adds is the
 // whole cost, so the loads run eight terms ahead of it (a plain loop exposes the shared-memory
 // latency once per unrolled group: 15-20 cycles per term instead of the add's 8).

@@ -573,10 +573,16 @@ template <class T, class F> __global__ void __launch_bounds__(WARP2D_WARPS * 32,
 
 template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_adaptive2d_cta(const Args<T> a)
 {
-    family_tables_init<T, F>();  // barrier inside: before any early return
     constexpr bool CMPL = is_cmpl2d<F>::value;
     __shared__ T red[64];
     __shared__ int s_done;
+    if (a.tail_idx != nullptr) {
+        // queue pass behind the warp pass: most calls leave nothing in the queue, and an empty pass should cost a
+        // launch, not a table set-up (the count is uniform over the grid)
+        pdl_wait_primary();  // the warp pass has completed: the queue is final and visible
+        if (*a.tail_count == 0) return;
+    }
+    family_tables_init<T, F>();  // barrier inside: before any divergent return
     unsigned char* dyn = fts_dyn_smem;
     NodePipe np;
     const int nmax = a.max_levels > 0 ? (2 << a.max_levels) : 2;
@@ -588,7 +594,6 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
         adaptive2d_group<T, F, CTA_THREADS>(a, blockIdx.x, threadIdx.x, smem, nmax, a.max_levels, red, &s_done, np);
         return;
     }
-    pdl_wait_primary();  // the warp pass has completed: the queue is final and visible
     const int count = *a.tail_count;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         adaptive2d_group<T, F, CTA_THREADS>(a, a.tail_idx[q], threadIdx.x, smem, nmax, a.max_levels, red, &s_done, np);

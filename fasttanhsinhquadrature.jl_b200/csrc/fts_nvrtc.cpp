@@ -26,6 +26,7 @@ extern const char fts_src_kernels[];  // fts_kernels.cuh
 extern const char fts_src_cta[];      // fts_kernels_cta.cuh
 extern const char fts_src_exp_table[];  // fts_exp_table.inc
 extern const char fts_src_log_table[];  // fts_log_table.inc
+extern const char fts_src_dd_tables[];  // fts_dd_tables.inc
 
 namespace {
 
@@ -86,6 +87,9 @@ void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
             const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") + ">";
             if (fixed) v.push_back({dt, KID_FIXED_TPI, fast, std::string("fts::") + fixed + targs});
             if (adapt) v.push_back({dt, KID_ADAPT_TPI, fast, std::string("fts::") + adapt + targs});
+            if (dt == FTS_DD64 && adapt)
+                for (int g2 = 0; g2 < 2; ++g2)
+                    v.push_back({dt, KID_ADAPT_GRP, g2, std::string("fts::k_adaptive1d_grp<fts::dd, FtsUserIntegrand, ") + (kind == FTS_KIND_1D_CMPL ? "true, " : "false, ") + (g2 ? "2>" : "4>")});
             if (kind == FTS_KIND_1D_CMPL && dt != FTS_DD64) v.push_back({dt, KID_FIXED_CMPL, fast, std::string("fts::k_fixed1d_cmpl_tpi") + targs});
             if (kind == FTS_KIND_1D || kind == FTS_KIND_1D_CMPL)
                 v.push_back({dt, KID_ADAPT_TAIL, fast, std::string("fts::k_adaptive1d_tail<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") +
@@ -136,10 +140,10 @@ int compile(const std::string& body, int kind, int nparams, Program* m, bool wan
     src += "\n    }\n};\n";
     if (kind == FTS_KIND_2D_CMPL) src += "namespace fts { template <> struct is_cmpl2d<FtsUserIntegrand> { static constexpr bool value = true; }; }\n";
 
-    const char* hdr_src[] = {fts_src_dd, fts_src_math, fts_src_kernels, fts_src_cta, fts_src_exp_table, fts_src_log_table};
-    const char* hdr_name[] = {"fts_dd.cuh", "fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh", "fts_exp_table.inc", "fts_log_table.inc"};
+    const char* hdr_src[] = {fts_src_dd, fts_src_math, fts_src_kernels, fts_src_cta, fts_src_exp_table, fts_src_log_table, fts_src_dd_tables};
+    const char* hdr_name[] = {"fts_dd.cuh", "fts_math.cuh", "fts_kernels.cuh", "fts_kernels_cta.cuh", "fts_exp_table.inc", "fts_log_table.inc", "fts_dd_tables.inc"};
     nvrtcProgram prog = nullptr;
-    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 6, hdr_src, hdr_name);
+    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "fts_user_integrand.cu", 7, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) return nvrtc_fail(r, "nvrtcCreateProgram", nullptr, log, loglen);
     add_specs(m->specs, kind, want_dd);
     for (auto& s : m->specs) {

@@ -8,6 +8,7 @@ void t_dd_sub(const double* a, const double* b, double* r) { dd v = dd(a[0], a[1
 void t_dd_mul(const double* a, const double* b, double* r) { dd v = dd(a[0], a[1]) * dd(b[0], b[1]); r[0] = v.hi; r[1] = v.lo; }
 void t_dd_div(const double* a, const double* b, double* r) { dd v = dd(a[0], a[1]) / dd(b[0], b[1]); r[0] = v.hi; r[1] = v.lo; }
 void t_dd_sqrt(const double* a, double* r) { dd v = fts::dd_sqrt(dd(a[0], a[1])); r[0] = v.hi; r[1] = v.lo; }
+void t_dd_rsqrt(const double* a, double* r) { dd v = fts::dd_rsqrt(dd(a[0], a[1])); r[0] = v.hi; r[1] = v.lo; }
 void t_dd_exp(const double* a, double* r) { dd v = fts::dd_exp(dd(a[0], a[1])); r[0] = v.hi; r[1] = v.lo; }
 void t_dd_log(const double* a, double* r) { dd v = fts::dd_log(dd(a[0], a[1])); r[0] = v.hi; r[1] = v.lo; }
 void t_dd_sin(const double* a, double* r) { dd v = fts::dd_sin(dd(a[0], a[1])); r[0] = v.hi; r[1] = v.lo; }

@@ -62,6 +62,7 @@ def test_dd_accuracy_against_mpmath(shim):
         upd("mul", abs(_val(_bi(shim, "t_dd_mul", a, b)) - (xa * yb)) / abs(xa * yb))
         upd("div", abs(_val(_bi(shim, "t_dd_div", a, b)) - (xa / yb)) / abs(xa / yb))
         upd("sqrt", abs(_val(_un(shim, "t_dd_sqrt", b)) - mpmath.sqrt(yb)) / mpmath.sqrt(yb))
+        upd("rsqrt", abs(_val(_un(shim, "t_dd_rsqrt", b)) * mpmath.sqrt(yb) - 1))
         upd("log", abs(_val(_un(shim, "t_dd_log", b)) - mpmath.log(yb)) / max(abs(mpmath.log(yb)), mpmath.mpf(1e-3)))
         e = _dd(mpmath.mpf(rng.uniform(-300, 300)) + mpmath.mpf(rng.random()) * mpmath.mpf(2) ** -60)
         upd("exp", abs(_val(_un(shim, "t_dd_exp", e)) - mpmath.exp(_val(e))) / mpmath.exp(_val(e)))
@@ -69,7 +70,8 @@ def test_dd_accuracy_against_mpmath(shim):
         upd("sin", abs(_val(_un(shim, "t_dd_sin", s)) - mpmath.sin(_val(s))))
         upd("cos", abs(_val(_un(shim, "t_dd_cos", s)) - mpmath.cos(_val(s))))
     assert worst["add"] < 1e-31 and worst["mul"] < 1e-31 and worst["div"] < 1e-31 and worst["sqrt"] < 2e-31
-    assert worst["log"] < 5e-30 and worst["exp"] < 2e-29 and worst["sin"] < 2e-28 and worst["cos"] < 2e-28
+    assert worst["rsqrt"] < 1e-31
+    assert worst["log"] < 1e-31 and worst["exp"] < 1e-31 and worst["sin"] < 2e-28 and worst["cos"] < 2e-28
 
 
 def test_dd_edge_cases_of_the_complement_tables(shim):
@@ -78,6 +80,10 @@ def test_dd_edge_cases_of_the_complement_tables(shim):
     mpmath.mp.prec = 250
     tiny = _dd("1e-310")
     assert abs(_un(shim, "t_dd_sqrt", tiny)[0] - 1e-155) < 1e-165
+    assert abs(_val(_un(shim, "t_dd_rsqrt", tiny)) * mpmath.sqrt(_val(tiny)) - 1) < 1e-30
+    assert abs(_val(_un(shim, "t_dd_rsqrt", _dd("1e305"))) * mpmath.sqrt(_val(_dd("1e305"))) - 1) < 1e-31
+    assert _un(shim, "t_dd_rsqrt", np.array([0.0, 0.0]))[0] == np.inf and np.isnan(_un(shim, "t_dd_rsqrt", np.array([-1.0, 0.0]))[0])
+    assert _un(shim, "t_dd_rsqrt", np.array([np.inf, 0.0]))[0] == 0.0
     lg = _val(_un(shim, "t_dd_log", tiny))
     assert abs(lg - mpmath.log(_val(tiny))) < mpmath.mpf("1e-27")
     inv = _bi(shim, "t_dd_div", _dd(-1), tiny)
