@@ -79,7 +79,7 @@ void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
     case FTS_KIND_1D_CMPL: adapt = "k_adaptive1d_cmpl_tpi"; adapt_cta = "k_adaptive1d_cmpl_cta"; break;
     case FTS_KIND_2D_CMPL: adapt = "k_adaptive2d_tpi"; adapt_cta = "k_adaptive2d_cta"; break;
     }
-    const int ndt = (kind == FTS_KIND_1D || kind == FTS_KIND_1D_CMPL) ? 3 : 2;  // Double64: 1D kinds
+    const int ndt = 3;  // float, double, Double64 (2D/3D Double64: thread per integral only)
     for (int dt = 0; dt < ndt; ++dt) {
         if ((dt == FTS_DD64) != want_dd) continue;
         for (int fast = 0; fast < 2; ++fast) {
@@ -87,7 +87,7 @@ void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
             const std::string targs = std::string("<") + tn[dt] + ", FtsUserIntegrand, " + (fast ? "true" : "false") + ">";
             if (fixed) v.push_back({dt, KID_FIXED_TPI, fast, std::string("fts::") + fixed + targs});
             if (adapt) v.push_back({dt, KID_ADAPT_TPI, fast, std::string("fts::") + adapt + targs});
-            if (dt == FTS_DD64 && adapt)
+            if (dt == FTS_DD64 && adapt && (kind == FTS_KIND_1D || kind == FTS_KIND_1D_CMPL))
                 for (int g2 = 0; g2 < 2; ++g2)
                     v.push_back({dt, KID_ADAPT_GRP, g2, std::string("fts::k_adaptive1d_grp<fts::dd, FtsUserIntegrand, ") + (kind == FTS_KIND_1D_CMPL ? "true, " : "false, ") + (g2 ? "2>" : "4>")});
             if (kind == FTS_KIND_1D_CMPL && dt != FTS_DD64) v.push_back({dt, KID_FIXED_CMPL, fast, std::string("fts::k_fixed1d_cmpl_tpi") + targs});

@@ -75,6 +75,28 @@ def to_dd(values) -> np.ndarray:
     return out
 
 
+def dd_add(a, b) -> np.ndarray:
+    """a + b of Double64 arrays on the host, the arithmetic of csrc/fts_dd.cuh operator+ (two TwoSums, two renormalisations)"""
+    a, b = np.atleast_1d(a), np.atleast_1d(b)
+
+    def two_sum(x, y):
+        s = x + y
+        bb = s - x
+        return s, (x - (s - bb)) + (y - bb)
+
+    def quick_two_sum(x, y):
+        s = x + y
+        return s, y - (s - x)
+
+    sh, sl = two_sum(a["hi"], b["hi"])
+    th, tl = two_sum(a["lo"], b["lo"])
+    sh, sl = quick_two_sum(sh, sl + th)
+    sh, sl = quick_two_sum(sh, sl + tl)
+    out = np.zeros(np.shape(sh), Double64)
+    out["hi"], out["lo"] = sh, sl
+    return out
+
+
 def dd_to_mpf(a):
     """Double64 array -> list of mpmath.mpf (exact hi+lo)."""
     import mpmath
@@ -847,11 +869,19 @@ def quad_split(f, c, low=None, up=None, *, rtol=None, atol=0, max_levels=None, c
     dt = _dt(T)
     ml = max_levels if max_levels is not None else {1: 16, 2: 8, 3: 5}[dim]
     nsub = 1 << dim
-    sub_rtol = None if rtol is None else rtol / nsub
-    sub_atol = atol / nsub
+    def div_tol(v):  # Double64 tolerances may be decimal strings / mpmath numbers
+        if isinstance(v, str) or type(v).__module__.split(".")[0] == "mpmath":
+            import mpmath
+            with mpmath.workprec(200):
+                return mpmath.mpf(v) / nsub
+        return v / nsub
+
+    sub_rtol = None if rtol is None else div_tol(rtol)
+    sub_atol = div_tol(atol)
     if dt == Double64:
-        raise FtsError(L.ERR_UNSUPPORTED, "quad_split for Double64 is not implemented")
-    cc = np.asarray(c, dt); lo = np.asarray(low, dt); hi = np.asarray(up, dt)
+        cc, lo, hi = (to_dd(v).reshape(np.shape(v) if np.ndim(v) else ()) for v in (c, low, up))
+    else:
+        cc = np.asarray(c, dt); lo = np.asarray(low, dt); hi = np.asarray(up, dt)
     if dim == 1:
         cc, lo, hi = np.broadcast_arrays(cc.reshape(-1), lo.reshape(-1), hi.reshape(-1))
         scalar = np.ndim(c) == 0 and np.ndim(low) == 0 and np.ndim(up) == 0
@@ -891,5 +921,5 @@ def quad_split(f, c, low=None, up=None, *, rtol=None, atol=0, max_levels=None, c
     vals = np.asarray(vals).reshape(nb, nsub)
     total = vals[:, 0].copy()
     for s in range(1, nsub):
-        total = total + vals[:, s]
+        total = dd_add(total, vals[:, s]) if dt == Double64 else total + vals[:, s]
     return total[0] if scalar else total

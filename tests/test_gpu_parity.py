@@ -1109,3 +1109,56 @@ def test_reference_kats_on_the_gpu(gpu, oracle):
                                   order="reference", full_output=True)
     ro = oracle.adaptive_nd("f64", 3, F["F3_EXP"], None, [-1.0] * 3, [1.0] * 3, 1e-9, 0.0, 5, c3o)
     assert r.levels[0] == ro.level and rel(r.value[0], ro.value) <= RTOL64 and int(gpu.evals_for_level(3, r.levels)[0]) == ro.evals
+
+
+def test_double64_2d_3d_thread_per_integral(gpu):
+    """adaptive_integrate_2D/3D, integrate2D/3D and quad / quad_split are generic in T<:Real (quad.jl:117,155,
+    212-215, 262-264) and the reference runs them with Double64: thread-per-integral Double64 kernels, checked
+    against closed forms at 1e-28 (parity unpinned: the reference holds no Double64 value) and against the
+    Float64 path at 1e-14."""
+    import mpmath
+    mpmath.mp.dps = 50
+    n = 48
+    rng = np.random.default_rng(3)
+    lo2 = -1.0 - rng.random((n, 2)); hi2 = 0.5 + rng.random((n, 2))
+    c2 = gpu.adaptive_cache_2D(gpu.Double64, max_levels=6)
+    r = gpu.adaptive_integrate_2D(gpu.Double64, gpu.builtin("exp_2d"), gpu.to_dd(lo2), gpu.to_dd(hi2), rtol="1e-28", max_levels=6, cache=c2, full_output=True)
+    r64 = gpu.adaptive_integrate_2D(np.float64, gpu.builtin("exp_2d"), lo2, hi2, rtol=1e-13, max_levels=6, full_output=True)
+    got = gpu.dd_to_mpf(r.value)
+    assert r.converged.all()
+    for i in range(n):
+        ex = mpmath.mpf(1)
+        for d in range(2):
+            ex *= mpmath.exp(mpmath.mpf(float(hi2[i, d]))) - mpmath.exp(mpmath.mpf(float(lo2[i, d])))
+        assert abs(got[i] - ex) <= mpmath.mpf("1e-28") * abs(ex), i
+        assert abs(float(got[i]) - r64.value[i]) <= 1e-13 * abs(r64.value[i])
+    # 3D: x^2 y^2 z^2 on boxes (exact at every level past the first few: tanh-sinh is not exact for polynomials,
+    # so a few levels are needed) and exp(x+y+z)
+    m = 8
+    lo3 = -1.0 - 0.5 * rng.random((m, 3)); hi3 = 0.5 + 0.5 * rng.random((m, 3))
+    c3 = gpu.adaptive_cache_3D(gpu.Double64, max_levels=4)  # one thread walks (2 * 32 + 1)^3 points: keep it to level 4
+    r3 = gpu.adaptive_integrate_3D(gpu.Double64, gpu.builtin("exp_3d"), gpu.to_dd(lo3), gpu.to_dd(hi3), rtol="1e-12", max_levels=4, cache=c3, full_output=True, warn=False)
+    got3 = gpu.dd_to_mpf(r3.value)
+    for i in range(m):
+        ex = mpmath.mpf(1)
+        for d in range(3):
+            ex *= mpmath.exp(mpmath.mpf(float(hi3[i, d]))) - mpmath.exp(mpmath.mpf(float(lo3[i, d])))
+        assert abs(got3[i] - ex) <= mpmath.mpf("1e-10") * abs(ex), (i, r3.levels[i])
+    # fixed grids: integrate2D / integrate3D with tanhsinh(Double64, N)
+    x, w, h = gpu.tanhsinh(gpu.Double64, 60)
+    v2 = gpu.integrate2D(gpu.builtin("x2py2"), gpu.to_dd([-1.0, -1.0]), gpu.to_dd([1.0, 1.0]), x, w, h)
+    assert abs(gpu.dd_to_mpf(v2)[0] - mpmath.mpf(8) / 3) < mpmath.mpf("1e-22")  # the N = 60 grid itself is good to ~2e-24 here
+    x3, w3, h3 = gpu.tanhsinh(gpu.Double64, 24)
+    v3 = gpu.integrate3D(gpu.builtin("x2y2z2"), gpu.to_dd([-1.0] * 3), gpu.to_dd([1.0] * 3), x3, w3, h3)
+    # N = 24 is a coarse grid: the point is the sum, not the quadrature error — x^2 y^2 z^2 separates into (2 h sum w_i x_i^2)^3
+    s1d = 2 * gpu.dd_to_mpf(h3)[0] * sum(wi * xi * xi for xi, wi in zip(gpu.dd_to_mpf(x3), gpu.dd_to_mpf(w3)))
+    assert abs(gpu.dd_to_mpf(v3)[0] - s1d ** 3) < mpmath.mpf("1e-28")
+    # quad_split in Double64: 1D and 2D
+    s1 = gpu.quad_split(gpu.builtin("exp"), gpu.to_dd([0.3]), gpu.to_dd([0.0]), gpu.to_dd([1.0]), rtol="1e-28")
+    assert abs(gpu.dd_to_mpf(s1)[0] - (mpmath.e - 1)) < mpmath.mpf("1e-28")
+    s2 = gpu.quad_split(gpu.builtin("exp_2d"), gpu.to_dd([[0.25, -0.5]]), gpu.to_dd([[-1.0, -1.0]]), gpu.to_dd([[1.0, 1.0]]), rtol="1e-26", max_levels=6)
+    assert abs(gpu.dd_to_mpf(s2)[0] - (mpmath.e - 1 / mpmath.e) ** 2) < mpmath.mpf("1e-25")
+    # a user integrand in Double64, 2D (NVRTC)
+    u = gpu.cuda_integrand("return exp(x) * exp(y);", "2d")
+    ru = gpu.adaptive_integrate_2D(gpu.Double64, u, gpu.to_dd([[-1.0, -1.0]]), gpu.to_dd([[1.0, 1.0]]), rtol="1e-28", max_levels=6, cache=c2)
+    assert abs(gpu.dd_to_mpf(ru)[0] - (mpmath.e - 1 / mpmath.e) ** 2) < mpmath.mpf("1e-27")
