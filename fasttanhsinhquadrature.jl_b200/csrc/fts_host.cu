@@ -83,6 +83,7 @@ int kind_dim(int kind)
     case FTS_KIND_2D: case FTS_KIND_2D_CMPL: return 2;
     case FTS_KIND_3D: return 3;
     }
+    if (kind > FTS_KIND_ND && kind <= FTS_KIND_ND + FTS_ND_MAX) return kind - FTS_KIND_ND;
     return 0;
 }
 bool kind_cmpl(int kind) { return kind == FTS_KIND_1D_CMPL || kind == FTS_KIND_2D_CMPL; }
@@ -877,11 +878,60 @@ template <class T> static void fill_cache_args(fts::Args<T>& a, fts_cache c)
     }
 }
 
+// generic n-D tensor product (kinds FTS_KIND_ND + D): gridDim.x CTAs per integral, sized to the (2n+1)^D points
+template <class T>
+static int run_fixed_nd(fts_tables t, fts_integrand f, const void* low, const void* up, int bstride, const void* params, int pstride,
+                        long long batch, void* out_value, cudaStream_t s)
+{
+    if (batch == 0) return FTS_OK;
+    if (batch > 65535) return set_error(FTS_ERR_INVALID_ARGUMENT, "n-D tensor products: at most 65535 integrals per call");
+    const int dim = kind_dim(f->kind);
+    const void* fn = integrand_kernel(f, t->dtype, KID_FIXED_ND, 1);
+    if (!fn) return set_error(FTS_ERR_UNSUPPORTED, "n-D tensor products: float32 / float64 NVRTC integrands");
+    const double m = 2.0 * t->n + 1.0;
+    double points = 1.0;
+    for (int d = 0; d < dim; ++d) points *= m;
+    if (points > 9.0e18) return set_error(FTS_ERR_INVALID_ARGUMENT, "n-D tensor product: (2N+1)^D exceeds 2^63 points");
+    // >= 8 points per thread, at most 4 CTAs per SM over the whole batch
+    double want = points / (fts::CTA_THREADS * 8.0);
+    const double cap = (double)g_prop.multiProcessorCount * 4.0 / (double)batch;
+    if (want > cap) want = cap;
+    if (want < 1.0) want = 1.0;
+    const unsigned blocks = (unsigned)want;
+    T* scratch = nullptr;
+    const size_t part = 2 * (size_t)blocks * batch;
+    FTS_CUDA(cudaMallocAsync((void**)&scratch, part * sizeof(T) + (size_t)batch * sizeof(unsigned int), s));
+    unsigned int* ticket = (unsigned int*)(scratch + part);
+    FTS_CUDA(cudaMemsetAsync(ticket, 0, (size_t)batch * sizeof(unsigned int), s));
+    fts::Args<T> a;
+    memset(&a, 0, sizeof a);
+    a.grid = (const fts::Node<T>*)t->d_grid;
+    a.n = t->n;
+    a.h = load_elem<T>(t->h);
+    a.low = (const T*)low; a.up = (const T*)up; a.bstride = bstride;
+    a.params = (const T*)params; a.pstride = pstride;
+    a.batch = batch;
+    a.value = (T*)out_value;
+    a.block_partials = scratch;
+    a.ticket = ticket;
+    const size_t smem = 2 * (size_t)(2 * t->n + 1) * sizeof(T);
+    if (int rc = ensure_dyn_smem(fn, smem)) return rc;
+    void* kargs[] = {&a};
+    FTS_CUDA(cudaLaunchKernel(fn, dim3(blocks, (unsigned)batch), dim3(fts::CTA_THREADS), kargs, smem, s));
+    g_launches.fetch_add(1);
+    FTS_CUDA(cudaFreeAsync(scratch, s));
+    return FTS_OK;
+}
+
 template <class T>
 static int run_fixed(fts_tables t, fts_integrand f, int order, const void* low, const void* up, int bstride, const void* params,
                      int pstride, long long batch, void* out_value, cudaStream_t s)
 {
     const int dim = kind_dim(f->kind);
+    if (f->kind > FTS_KIND_ND) {
+        if constexpr (sizeof(T) == 16) return set_error(FTS_ERR_UNSUPPORTED, "n-D tensor products: float32 / float64");
+        else return run_fixed_nd<T>(t, f, low, up, bstride, params, pstride, batch, out_value, s);
+    }
     const void* fn_cta = t->dtype == FTS_DD64 ? nullptr : integrand_kernel(f, t->dtype, KID_FIXED_CTA, 1);
     const size_t smem = dim == 1 ? 0 : (size_t)(dim == 2 ? 5 : fts::SM3_ARRAYS) * t->n * sizeof(T);
     const bool cta_ok = fn_cta && smem <= dyn_smem_limit();

@@ -25,7 +25,8 @@ enum KernelId : int {
     KID_ADAPT_WARP = 10,   // k_adaptive2d_warp               warp per integral, shallow levels (large 2D batches, FAST only)
     KID_ADAPT_BUCKET = 11, // k_adaptive1d_bucket             warp tasks over bound-ordered chunks (1D exp families, Float64, arbitrary parameter order)
     KID_ADAPT_GRP = 12,    // k_adaptive1d_grp                a group of 4 lanes per integral (Double64, 1D kinds); `fast` = 1: groups of 2
-    KID_COUNT = 13
+    KID_FIXED_ND = 13,     // k_fixed_nd                      generic n-D tensor product, fixed grid (NVRTC integrands of kind FTS_KIND_ND + D)
+    KID_COUNT = 14
 };
 
 struct KernelEntry {

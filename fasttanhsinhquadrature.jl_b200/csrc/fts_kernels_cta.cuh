@@ -938,6 +938,103 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_fix
     if (tid == 0) a.value[b] = (s.dx * s.dy * s.dz * (a.h * a.h * a.h)) * tot.value();
 }
 
+// ---------------------------------------------------------------- generic n-D tensor product ----
+// integrate1D/2D/3D's weighted node sum on a D-dimensional box (the reference's stated next step, JOSS paper.md:121):
+// sum over the (2n+1)^D points of prod_d w_{i_d} f(x0 + dx * xi_{i_d}), times prod_d dx_d * h^D.  The signed node
+// table (index 0 = centre, 2k-1 / 2k = +-x_k) sits in shared memory; gridDim.x CTAs per integral (blockIdx.y) walk
+// the flat point index with a stride, carrying the D base-(2n+1) digits instead of dividing; compensated partials
+// per CTA, the last CTA of an integral merges them in CTA order.  F::eval(const T* x, const T* p).
+template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS) k_fixed_nd(const Args<T> a)
+{
+    __shared__ T red[64];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const long long b = blockIdx.y;
+    const int m = 2 * a.n + 1;
+    T* xs = reinterpret_cast<T*>(fts_dyn_smem);
+    T* ws = xs + m;
+    for (int i = tid; i < m; i += blockDim.x) {
+        if (i == 0) {
+            xs[0] = num<T>::zero();
+            ws[0] = num<T>::half_pi();
+        } else {
+            const Node<T> nd = a.grid[(i - 1) >> 1];
+            xs[i] = (i & 1) ? nd.x : -nd.x;
+            ws[i] = nd.w;
+        }
+    }
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    const T half = num<T>::half();
+    T dx[D], x0[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const T lo = a.low[b * a.bstride + d], hi = a.up[b * a.bstride + d];
+        dx[d] = half * (hi - lo);
+        x0[d] = half * (hi + lo);
+    }
+    __syncthreads();
+    unsigned long long total = 1ULL;
+#pragma unroll
+    for (int d = 0; d < D; ++d) total *= (unsigned long long)m;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + tid;
+    int dig[D], sdig[D];
+    {
+        unsigned long long q = t, r = stride;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            dig[d] = (int)(q % (unsigned long long)m); q /= (unsigned long long)m;
+            sdig[d] = (int)(r % (unsigned long long)m); r /= (unsigned long long)m;
+        }
+    }
+    Comp<T> acc;
+    for (; t < total; t += stride) {
+        T x[D];
+        T w = num<T>::one();
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            x[d] = fm::fma(dx[d], xs[dig[d]], x0[d]);
+            w = w * ws[dig[d]];
+        }
+        acc.add(w * F::template eval<T, true>(x, p));
+        int carry = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            int v = dig[d] + sdig[d] + carry;
+            carry = v >= m ? 1 : 0;
+            dig[d] = v - (carry ? m : 0);
+        }
+    }
+    const Comp<T> bsum = block_reduce(acc, red);
+    T* partials = a.block_partials + 2 * (size_t)b * gridDim.x;
+    if (tid == 0) {
+        partials[2 * blockIdx.x] = bsum.s;
+        partials[2 * blockIdx.x + 1] = bsum.c;
+        __threadfence();
+        const unsigned int k = atomicAdd(a.ticket + b, 1u);
+        s_last = (k == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Comp<T> tot;
+    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+        Comp<T> o;
+        o.s = __ldcg(partials + 2 * i);
+        o.c = __ldcg(partials + 2 * i + 1);
+        tot.merge(o);
+    }
+    tot = block_reduce(tot, red);
+    if (tid == 0) {
+        T scale = num<T>::one();
+#pragma unroll
+        for (int d = 0; d < D; ++d) scale = scale * (dx[d] * a.h);
+        a.value[b] = scale * tot.value();
+        a.ticket[b] = 0u;
+    }
+}
+
 // Stop test after the partials of all ranks are known (adaptive.jl:693-700): one thread, identical arithmetic
 // on every rank.  part(r) = rank r's compensated (s, c) of the level, merged in rank order.
 // state = {s_total.s, s_total.c, old_res, value, err, done, level_used, h}

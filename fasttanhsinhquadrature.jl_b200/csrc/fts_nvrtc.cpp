@@ -65,6 +65,7 @@ const char* kind_args(int kind)
     case FTS_KIND_1D_CMPL: return "T x, T bmx, T xma";
     case FTS_KIND_2D_CMPL: return "T x, T y, T bmx, T xma, T dmy, T ymc";
     }
+    if (kind > FTS_KIND_ND && kind <= FTS_KIND_ND + FTS_ND_MAX) return "const T* x";  // x[0] ... x[ND - 1]
     return nullptr;
 }
 
@@ -78,6 +79,13 @@ void add_specs(std::vector<KernelSpec>& v, int kind, bool want_dd)
     case FTS_KIND_3D: fixed = "k_fixed3d_tpi"; adapt = "k_adaptive3d_tpi"; adapt_cta = "k_adaptive3d_cta"; fixed_cta = "k_fixed3d_cta"; break;
     case FTS_KIND_1D_CMPL: adapt = "k_adaptive1d_cmpl_tpi"; adapt_cta = "k_adaptive1d_cmpl_cta"; break;
     case FTS_KIND_2D_CMPL: adapt = "k_adaptive2d_tpi"; adapt_cta = "k_adaptive2d_cta"; break;
+    }
+    if (kind > FTS_KIND_ND) {  // generic n-D tensor product: fixed grids, float / double
+        if (want_dd) return;
+        const std::string d = std::to_string(kind - FTS_KIND_ND);
+        v.push_back({FTS_F32, KID_FIXED_ND, 1, "fts::k_fixed_nd<float, FtsUserIntegrand, " + d + ">"});
+        v.push_back({FTS_F64, KID_FIXED_ND, 1, "fts::k_fixed_nd<double, FtsUserIntegrand, " + d + ">"});
+        return;
     }
     const int ndt = 3;  // float, double, Double64 (2D/3D Double64: thread per integral only)
     for (int dt = 0; dt < ndt; ++dt) {
@@ -135,6 +143,7 @@ int compile(const std::string& body, int kind, int nparams, Program* m, bool wan
     std::string src;
     src += "#include \"fts_kernels.cuh\"\n#include \"fts_kernels_cta.cuh\"\n";
     src += "struct FtsUserIntegrand {\n    static constexpr int NP = " + std::to_string(nparams) + ";\n";
+    if (kind > FTS_KIND_ND) src += "    static constexpr int ND = " + std::to_string(kind - FTS_KIND_ND) + ";\n";
     src += std::string("    template <class T, bool FAST> static __device__ __forceinline__ T eval(") + args + ", const T* p)\n    {\n";
     src += body;
     src += "\n    }\n};\n";

@@ -10,7 +10,7 @@ from .api import (FAMILIES, AdaptiveCache, AdaptiveResult, DeviceTables, Converg
                   adaptive_cache_2D, adaptive_cache_2D_cmpl, adaptive_cache_3D, adaptive_integrate_1D, adaptive_integrate_1D_avx,
                   adaptive_integrate_1D_cmpl, adaptive_integrate_1D_cmpl_avx, adaptive_integrate_2D, adaptive_integrate_2D_avx,
                   adaptive_integrate_2D_cmpl, adaptive_integrate_3D, adaptive_integrate_3D_avx, builtin, cuda_integrand, dd_add, dd_to_mpf,
-                  device_info, init, integrate1D, integrate1D_avx, integrate1D_cmpl, integrate2D, integrate2D_avx, integrate3D, integrate3D_avx,
+                  device_info, init, integrate1D, integrate1D_avx, integrate1D_cmpl, integrate2D, integrate2D_avx, integrate3D, integrate3D_avx, integrateND,
                   launch_count, measure_fma_peak, evaluate, pinned_empty, adaptive_batch_dev, adaptive_batch_host, evals_for_level, quad, quad_cmpl, quad_split, t_w_max, t_x_max, tanhsinh, tanhsinh_opt, hopt, hmax, tmax, to_dd)
 
 # the 21 names exported by the reference (src/FastTanhSinhQuadrature.jl:44-51)

@@ -22,6 +22,7 @@ OPT_QUAD_EDGE_RULES = 1
 OPT_FORCE_DEPTH = 2
 FLAG_CONVERGED, FLAG_MAX_LEVELS, FLAG_ZERO_WIDTH, FLAG_FLIPPED = 1, 2, 4, 8
 KIND_1D, KIND_2D, KIND_3D, KIND_1D_CMPL, KIND_2D_CMPL = 1, 2, 3, 4, 5
+KIND_ND, ND_MAX = 16, 8  # generic n-D tensor products: kind = KIND_ND + D
 
 
 class FtsError(RuntimeError):

@@ -215,6 +215,8 @@ class Integrand:
 
     @property
     def dim(self) -> int:
+        if self.kind > L.KIND_ND:
+            return self.kind - L.KIND_ND
         return {L.KIND_1D: 1, L.KIND_1D_CMPL: 1, L.KIND_2D: 2, L.KIND_2D_CMPL: 2, L.KIND_3D: 3}[self.kind]
 
     def __del__(self):
@@ -251,14 +253,20 @@ _KIND_BY_NAME = {"1d": L.KIND_1D, "2d": L.KIND_2D, "3d": L.KIND_3D, "1d_cmpl": L
                  "2d_cmpl": L.KIND_2D_CMPL}
 
 
-def cuda_integrand(body: str, kind="1d", nparams: int = 0, name: str = "user") -> Integrand:
+def cuda_integrand(body: str, kind="1d", nparams: int = 0, name: str = "user", dim: Optional[int] = None) -> Integrand:
     """Compile a user integrand with NVRTC for sm_100a.
 
     `body` is the body of ``template<class T> __device__ T f(ARGS, const T* p)`` with ARGS =
     ``T x`` | ``T x, T y`` | ``T x, T y, T z`` | ``T x, T bmx, T xma`` |
     ``T x, T y, T bmx, T xma, T dmy, T ymc`` — e.g. ``"return exp(-p[0]*x*x);"``.
+    kind="nd", dim=D (1 <= D <= 8): ARGS = ``const T* x`` (x[0] ... x[D-1]; ``ND`` is D) for integrateND.
     """
-    k = _KIND_BY_NAME[kind] if isinstance(kind, str) else int(kind)
+    if kind == "nd":
+        if dim is None or not 1 <= int(dim) <= L.ND_MAX:
+            raise ArgumentError(L.ERR_INVALID_ARGUMENT, f"cuda_integrand(kind='nd') needs dim = 1 ... {L.ND_MAX}")
+        k = L.KIND_ND + int(dim)
+    else:
+        k = _KIND_BY_NAME[kind] if isinstance(kind, str) else int(kind)
     h = C.c_void_p()
     log = C.create_string_buffer(16384)
     rc = L.lib.fts_integrand_nvrtc(body.encode(), k, nparams, C.byref(h), log, len(log))
@@ -497,6 +505,22 @@ def integrate3D(f, *args, params=None, order="reference"):
         return _integrate(f, 3, [-1.0] * 3, [1.0] * 3, x, w, h, params, order, "integrate3D")
     low, up, x, w, h = args
     return _integrate(f, 3, low, up, x, w, h, params, order, "integrate3D")
+
+
+def integrateND(f, *args, params=None):
+    """integrateND(f, x, w, h) | integrateND(f, low, up, x, w, h): the tensor-product node sum of integrate1D/2D/3D on a
+    D-dimensional box, D = f.dim <= 8 (the generalisation the reference's paper names as its next step,
+    JOSS_paper/paper.md:121; no reference implementation exists).  f = cuda_integrand(body, kind="nd", dim=D);
+    float32 / float64; reassociated summation with compensated partials (the `_avx` flavour).  Build the grid with
+    tanhsinh(T, N, D=D): the weight window depends on D (core.jl:207-221)."""
+    if not isinstance(f, Integrand) or f.kind <= L.KIND_ND:
+        raise DimensionMismatch(L.ERR_DIMENSION_MISMATCH, "integrateND needs an integrand of kind 'nd' (cuda_integrand(body, kind='nd', dim=D))")
+    D = f.dim
+    if len(args) == 3:
+        x, w, h = args
+        return _integrate(f, D, [-1.0] * D, [1.0] * D, x, w, h, params, "fast", "integrateND")
+    low, up, x, w, h = args
+    return _integrate(f, D, low, up, x, w, h, params, "fast", "integrateND")
 
 
 def integrate3D_avx(f, *args, params=None):

@@ -50,6 +50,7 @@ enum {
 
 /* ---- element types (dtype ∈ {f32,f64,dd64}) ------------------------------------ */
 typedef enum { FTS_F32 = 0, FTS_F64 = 1, FTS_DD64 = 2 } fts_dtype;
+#define FTS_ND_MAX 8
 
 /* Double64 element: unevaluated sum hi+lo, |lo| <= ulp(hi)/2 (DoubleFloats.jl layout). */
 typedef struct { double hi, lo; } fts_dd;
@@ -60,7 +61,13 @@ typedef enum {
        and integrate*D / adaptive_integrate_* compute; quad.jl:49,117,155,309), no FMA
        contraction: one thread per integral for large batches; for a few 2D/3D integrals (and
        long 1D grids) one CTA per integral evaluates the terms in parallel and adds them in the
-       same order — bit-identical results either way. */
+       same order — bit-identical results either way.
+       Double64 (FTS_DD64) is the exception: nothing pins its summation order (the reference holds
+       no Double64 value; tolerance 1e-28 against a 1e-32 format), so 1D batches are summed by
+       groups of 4 lanes per integral (lane g adds the nodes g, g+4, ... of a level in index order,
+       the four partial sums are added in lane order; FTS_B200_DD_GROUP=1 restores one thread per
+       integral) and levels past 7 by a per-tile tree.  The result depends on neither the batch
+       nor the launch.  Double64 2D/3D integrals run one thread each in the reference's order. */
     FTS_ORDER_REFERENCE = 0,
     /* reassociated + FMA, compensated merges (the analogue of the `_avx`/@turbo twins,
        integrate1D.jl:124-147, adaptive.jl:94-133 ...): cooperative CTA/grid per integral. */
@@ -95,7 +102,11 @@ typedef enum {
     FTS_KIND_2D = 2,      /* f(x,y)               integrate2D*, adaptive_integrate_2D*                */
     FTS_KIND_3D = 3,      /* f(x,y,z)             integrate3D*, adaptive_integrate_3D*                */
     FTS_KIND_1D_CMPL = 4, /* f(x, b-x, x-a)       adaptive_integrate_1D_cmpl*, quad_cmpl              */
-    FTS_KIND_2D_CMPL = 5  /* f(x,y, b-x,x-a, d-y,y-c)  tensor extension used by BASELINE config C    */
+    FTS_KIND_2D_CMPL = 5, /* f(x,y, b-x,x-a, d-y,y-c)  tensor extension used by BASELINE config C    */
+    /* f(const T* x) on a D-dimensional box, 1 <= D <= FTS_ND_MAX: kind = FTS_KIND_ND + D.  The generic n-D tensor
+       product the reference's paper names as its next step (JOSS_paper/paper.md:121) — an extension: NVRTC
+       integrands only, fixed grids (fts_integrate_batch), f32/f64, reassociated (FAST) summation. */
+    FTS_KIND_ND = 16
 } fts_kind;
 
 /* ---- builtin integrand families ----------------------------------------------------------- */

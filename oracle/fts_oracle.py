@@ -246,6 +246,25 @@ class Oracle:
         return getattr(self.lib, f"fts_or_integrate{D}d_{dtype}")(
             fam, _ptr(pa), cb, _ptr(lo), _ptr(hi), _ptr(x), _ptr(w), len(x), ct(h))
 
+    @staticmethod
+    def integrate_tensor_generic(fn, low, up, x, w, h):
+        """The tensor-product rule of integrate2D / integrate3D (src/integrate2D.jl:91-124, src/integrate3D.jl:150-207)
+        written for any dimension D = len(low): sum over the (2n+1)^D points (centre weight pi/2, nodes +-x_k) of
+        prod_d w f(x0 + dx * xi), times prod_d dx_d * h^D.  The reference has no D > 3 (JOSS_paper/paper.md:121 names it
+        as future work): this numpy statement is pinned by agreeing with integrate_nd for D = 2, 3.  `fn` takes an array
+        [D, npoints] and returns [npoints]; float64, math.fsum (exact) summation.  Test infrastructure only."""
+        import math
+        lo = np.asarray(low, np.float64); hi = np.asarray(up, np.float64)
+        D = lo.shape[0]
+        xs = np.concatenate([[0.0], np.stack([np.asarray(x, np.float64), -np.asarray(x, np.float64)], 1).reshape(-1)])
+        ws = np.concatenate([[math.pi / 2], np.repeat(np.asarray(w, np.float64), 2)])
+        dx, x0 = 0.5 * (hi - lo), 0.5 * (hi + lo)
+        grids = np.meshgrid(*[np.arange(xs.shape[0])] * D, indexing="ij")
+        idx = np.stack([g.reshape(-1) for g in grids])
+        pts = x0[:, None] + dx[:, None] * xs[idx]
+        wt = np.prod(ws[idx], axis=0)
+        return float(np.prod(dx) * float(h) ** D * math.fsum(wt * fn(pts)))
+
     # ------------------------------------------------------------------ adaptive ------------
     def _res(self, dtype):
         return _Res32() if dtype.startswith("f32") else _Res64()

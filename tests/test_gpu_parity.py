@@ -1162,3 +1162,46 @@ def test_double64_2d_3d_thread_per_integral(gpu):
     u = gpu.cuda_integrand("return exp(x) * exp(y);", "2d")
     ru = gpu.adaptive_integrate_2D(gpu.Double64, u, gpu.to_dd([[-1.0, -1.0]]), gpu.to_dd([[1.0, 1.0]]), rtol="1e-28", max_levels=6, cache=c2)
     assert abs(gpu.dd_to_mpf(ru)[0] - (mpmath.e - 1 / mpmath.e) ** 2) < mpmath.mpf("1e-27")
+
+
+def test_generic_nd_tensor_product(gpu, oracle):
+    """integrateND: the n-D generalisation of integrate1D/2D/3D (JOSS_paper/paper.md:121, extension — no reference
+    values exist): D = 2, 3 against the GPU's own integrate2D/3D kernels and the restated reference rules; D = 4, 5, 6
+    against the numpy statement of the rule (oracle.integrate_tensor_generic) and separable closed forms."""
+    body_exp = "T s = x[0]; for (int d = 1; d < ND; ++d) s = s + x[d]; return exp(s);"
+    x, w, h = gpu.tanhsinh(np.float64, 12)
+    # D = 2, 3: same grid through the 2D / 3D kernels and the oracle
+    for D, fam, name in ((2, F["F2_EXP"], "exp_2d"), (3, F["F3_EXP"], "exp_3d")):
+        low, up = [-2.0, -1.0, 0.0][:D], [3.0, 2.0, 4.0][:D]
+        f = gpu.cuda_integrand(body_exp, "nd", dim=D)
+        v = gpu.integrateND(f, low, up, x, w, h)
+        ref = oracle.integrate_nd("f64x", D, fam, None, low, up, x, w, h)
+        own = (gpu.integrate2D_avx if D == 2 else gpu.integrate3D_avx)(gpu.builtin(name), low, up, x, w, h)
+        assert abs(v - ref) <= 1e-14 * abs(ref) and abs(v - own) <= 1e-14 * abs(ref), (D, v, ref, own)
+    # D = 4 (9^4 = 6 561 points per box), non-separable integrand with a parameter, batch of boxes
+    rng = np.random.default_rng(5)
+    f4 = gpu.cuda_integrand("T r2 = T(0); for (int d = 0; d < ND; ++d) r2 = r2 + x[d] * x[d]; return exp(-p[0] * r2) / (T(1) + x[0] * x[3]);", "nd", dim=4, nparams=1)
+    x8, w8, h8 = gpu.tanhsinh(np.float64, 8, D=4)
+    lo = -0.5 - 0.4 * rng.random((6, 4)); hi = 0.2 + 0.7 * rng.random((6, 4)); al = 0.5 + rng.random(6)
+    v4 = gpu.integrateND(f4, lo, hi, x8, w8, h8, params=al)
+    for i in range(6):
+        ref = oracle.integrate_tensor_generic(lambda p: np.exp(-al[i] * (p ** 2).sum(0)) / (1 + p[0] * p[3]), lo[i], hi[i], x8, w8, h8)
+        assert abs(v4[i] - ref) <= 1e-14 * abs(ref), (i, v4[i], ref)
+    # D = 5 (41^5 = 116 M points), D = 6 (21^6 = 86 M): exp(sum x) separates into the 1D rule to the power D
+    for D, N in ((5, 40), (6, 20)):
+        xd, wd, hd = gpu.tanhsinh(np.float64, N, D=D)
+        f = gpu.cuda_integrand(body_exp, "nd", dim=D)
+        v = gpu.integrateND(f, [-1.0] * D, [1.0] * D, xd, wd, hd)
+        s1 = hd * (math.pi / 2 + float(np.sum(wd * (np.exp(xd) + np.exp(-xd)))))
+        assert abs(v - s1 ** D) <= 1e-13 * s1 ** D, (D, v, s1 ** D)
+        assert abs(v - (math.e - 1 / math.e) ** D) <= 1e-3 * (math.e - 1 / math.e) ** D
+    # Float32 and argument checks
+    x32, w32, h32 = gpu.tanhsinh(np.float32, 8, D=4)
+    f32 = gpu.cuda_integrand(body_exp, "nd", dim=4)
+    v32 = gpu.integrateND(f32, np.float32([-1] * 4), np.float32([1] * 4), x32, w32, h32)
+    s32 = float(h32) * (math.pi / 2 + float(np.sum(w32.astype(np.float64) * (np.exp(x32.astype(np.float64)) + np.exp(-x32.astype(np.float64))))))
+    assert abs(float(v32) - s32 ** 4) <= 2e-6 * s32 ** 4
+    with pytest.raises(gpu.DimensionMismatch):
+        gpu.integrateND(f32, [-1.0] * 3, [1.0] * 3, x, w, h)
+    with pytest.raises(gpu.ArgumentError):
+        gpu.cuda_integrand(body_exp, "nd", dim=9)

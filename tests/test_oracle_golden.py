@@ -310,3 +310,20 @@ def test_integrate1d_cmpl_kat(oracle):
     x32, w32, h32 = oracle.tanhsinh("f32", 60)
     v32 = oracle.integrate1d_cmpl("f32", F["C1_EXP_PLUS"], None, x32, w32, h32)     # exp(x) + (1-x) + (1+x): e - 1/e + 4
     assert abs(v32 - (math.e - 1 / math.e + 4)) < 1e-4
+
+
+def test_generic_tensor_rule_agrees_with_the_reference_rules_for_2d_3d(oracle):
+    """oracle.integrate_tensor_generic (checker of the n-D extension, integrateND) against the restated
+    integrate2D / integrate3D on the same grids: the generic statement is pinned where the reference exists."""
+    x, w, h = oracle.tanhsinh("f64", 12)
+    low2, up2 = [-2.0, -1.0], [3.0, 2.0]
+    v2 = oracle.integrate_nd("f64", 2, F["F2_EXP"], None, low2, up2, x, w, h)
+    g2 = oracle.integrate_tensor_generic(lambda p: np.exp(p[0] + p[1]), low2, up2, x, w, h)
+    assert abs(v2 - g2) <= 4e-15 * abs(v2)
+    low3, up3 = [-2.0, -1.0, 0.0], [3.0, 2.0, 4.0]
+    v3 = oracle.integrate_nd("f64", 3, F["F3_X2Y2Z2"], None, low3, up3, x, w, h)
+    g3 = oracle.integrate_tensor_generic(lambda p: (p[0] * p[1] * p[2]) ** 2, low3, up3, x, w, h)
+    assert abs(v3 - g3) <= 4e-15 * abs(v3)
+    v3e = oracle.integrate_nd("f64", 3, F["F3_EXP"], None, low3, up3, x, w, h)
+    g3e = oracle.integrate_tensor_generic(lambda p: np.exp(p[0] + p[1] + p[2]), low3, up3, x, w, h)
+    assert abs(v3e - g3e) <= 4e-15 * abs(v3e)
