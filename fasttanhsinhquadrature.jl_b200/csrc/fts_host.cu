@@ -892,8 +892,8 @@ static int run_fixed_nd(fts_tables t, fts_integrand f, const void* low, const vo
     double points = 1.0;
     for (int d = 0; d < dim; ++d) points *= m;
     if (points > 9.0e18) return set_error(FTS_ERR_INVALID_ARGUMENT, "n-D tensor product: (2N+1)^D exceeds 2^63 points");
-    // >= 8 points per thread, at most 4 CTAs per SM over the whole batch
-    double want = points / (fts::CTA_THREADS * 8.0);
+    // >= 2 runs of up to 32 points per thread, at most 4 CTAs per SM over the whole batch
+    double want = points / m * ceil(m / 32.0) / (fts::CTA_THREADS * 2.0);
     const double cap = (double)g_prop.multiProcessorCount * 4.0 / (double)batch;
     if (want > cap) want = cap;
     if (want < 1.0) want = 1.0;

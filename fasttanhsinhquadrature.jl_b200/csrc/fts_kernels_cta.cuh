@@ -974,9 +974,15 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
         x0[d] = half * (hi + lo);
     }
     __syncthreads();
-    unsigned long long total = 1ULL;
+    // work unit = (outer point: axes 1 ... D-1, chunk of <= 32 points along axis 0): the outer coordinates and
+    // weight product are formed once per unit, the flat unit index is walked by carrying its digits
+    // (digit 0 = chunk, base nch; digits 1 ... D-1 = outer axes, base m) instead of dividing
+    constexpr int ND_RUN_MAX = 32;
+    const int nch = (m + ND_RUN_MAX - 1) / ND_RUN_MAX;
+    const int ND_RUN = (m + nch - 1) / nch;  // equal chunks (161 points: 6 x 27, not 5 x 32 + 1)
+    unsigned long long total = (unsigned long long)nch;
 #pragma unroll
-    for (int d = 0; d < D; ++d) total *= (unsigned long long)m;
+    for (int d = 1; d < D; ++d) total *= (unsigned long long)m;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + tid;
     int dig[D], sdig[D];
@@ -984,26 +990,34 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
         unsigned long long q = t, r = stride;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            dig[d] = (int)(q % (unsigned long long)m); q /= (unsigned long long)m;
-            sdig[d] = (int)(r % (unsigned long long)m); r /= (unsigned long long)m;
+            const unsigned long long base = d == 0 ? (unsigned long long)nch : (unsigned long long)m;
+            dig[d] = (int)(q % base); q /= base;
+            sdig[d] = (int)(r % base); r /= base;
         }
     }
     Comp<T> acc;
     for (; t < total; t += stride) {
         T x[D];
-        T w = num<T>::one();
+        T wo = num<T>::one();
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
+        for (int d = 1; d < D; ++d) {
             x[d] = fm::fma(dx[d], xs[dig[d]], x0[d]);
-            w = w * ws[dig[d]];
+            wo = wo * ws[dig[d]];
         }
-        acc.add(w * F::template eval<T, true>(x, p));
+        const int i0 = dig[0] * ND_RUN, i1 = i0 + ND_RUN < m ? i0 + ND_RUN : m;
+        T run = num<T>::zero();
+        for (int i = i0; i < i1; ++i) {
+            x[0] = fm::fma(dx[0], xs[i], x0[0]);
+            run = fm::fma(ws[i], F::template eval<T, true>(x, p), run);
+        }
+        acc.add(wo * run);
         int carry = 0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
+            const int base = d == 0 ? nch : m;
             int v = dig[d] + sdig[d] + carry;
-            carry = v >= m ? 1 : 0;
-            dig[d] = v - (carry ? m : 0);
+            carry = v >= base ? 1 : 0;
+            dig[d] = v - (carry ? base : 0);
         }
     }
     const Comp<T> bsum = block_reduce(acc, red);

@@ -287,6 +287,20 @@ def case_edev(reps):
         emit(case="E-device", family=name, batch=n, ms=t * 1e3, integrals_per_s=n / t, gevals_per_s=evals / t / 1e9, levels=np.bincount(levels).tolist())
 
 
+def case_nd(reps):
+    """integrateND (n-D extension): exp(sum x) on [-1,1]^D through the host-buffer call (wall clock incl. the
+    synchronisation; 16 B of bounds per axis in, one value out); flop/eval = 29 (exp) + 2 D (coordinates, weight) + 7"""
+    body = "T s = x[0]; for (int d = 1; d < ND; ++d) s = s + x[d]; return exp(s);"
+    for D, N in ((4, 160), (5, 60), (6, 28)):
+        x, w, h = fts.tanhsinh(np.float64, N, D=D)
+        f = fts.cuda_integrand(body, "nd", dim=D)
+        t, v = best_of(lambda: fts.integrateND(f, [-1.0] * D, [1.0] * D, x, w, h), max(3, reps // 2))
+        pts = (2 * len(x) + 1) ** D
+        s1 = h * (math.pi / 2 + float(np.sum(w * (np.exp(x) + np.exp(-x)))))
+        emit(case="ND", D=D, N=N, points=pts, ms=t * 1e3, gevals_per_s=pts / t / 1e9, rel_err_vs_separable_sum=abs(v - s1 ** D) / s1 ** D,
+             fp64_frac_nominal=pts / t * (36 + 2 * D) / 1e12 / FP64_PEAK)
+
+
 def main():
     global FP64_PEAK
     ap = argparse.ArgumentParser()
@@ -297,7 +311,7 @@ def main():
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
     emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
     for c in args.cases.split(","):
-        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "Cdev": case_cdev, "D": case_d, "Dk": case_dk, "E": case_e, "Edev": case_edev}[c](args.reps)
+        {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "Cdev": case_cdev, "D": case_d, "Dk": case_dk, "E": case_e, "Edev": case_edev, "ND": case_nd}[c](args.reps)
 
 
 if __name__ == "__main__":
