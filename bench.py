@@ -20,6 +20,8 @@ Prints ONE JSON line (rank 0).  Besides the contract's keys the line carries
   permuted      the same workload with the parameter set shuffled (seed 0)
   sharded3d     BASELINE configs[3]: ONE large 3D integral sharded over the N GPUs (the only path
                 with an exchange step), fused peer-memory exchange and NCCL all-gather variants
+  other_configs BASELINE configs[2] (4096 2D complement boxes, FP64 / FP32) and configs[4] (65 536 Double64
+                quad_cmpl integrals): device-resident, CUDA events (tools/bench_configs.py cases Cdev, Edev)
   cpu_baseline  the CPU port on the box's host cores (scalar = what `quad` runs; value_avx = the
                 @turbo twin)
 """
@@ -352,6 +354,7 @@ def main():
     ap.add_argument("--no-sharded3d", action="store_true", help="skip the sharded single-3D-integral record (BASELINE configs[3])")
     ap.add_argument("--sharded-levels", default="8,9", help="forced depths of the sharded 3D record")
     ap.add_argument("--no-host-link", action="store_true", help="skip the host-link ceiling probe")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the device-timed records of BASELINE configs C and E")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global PERMUTE
@@ -523,6 +526,21 @@ def main():
         except Exception as exc:  # pragma: no cover
             sharded = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- BASELINE configs[2] and [4] (C: 4096 2D complement boxes, FP64 and FP32; E: 65 536 Double64 quad_cmpl
+    # integrals), device-resident inputs, CUDA events, rank 0: the same code as tools/bench_configs.py --cases Cdev,Edev
+    other = None
+    if rank == 0 and not args.no_other_configs:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs as bc
+            bc.QUIET, bc.FP64_PEAK = True, peak["tflops"]
+            del bc.RECORDS[:]
+            bc.case_cdev(10)
+            bc.case_edev(5)
+            other = list(bc.RECORDS)
+        except Exception as exc:  # pragma: no cover
+            other = {"error": f"{type(exc).__name__}: {exc}"}
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
@@ -592,7 +610,7 @@ def main():
             "gevals_per_s": gevals, "evals_per_integral_mean": evals_per_step / n, "level_histogram": lv_hist, "converged": conv,
             "wall_s_timed_region": wall, "step_ms_min": min(step_ms), "step_ms_median": sorted(step_ms)[len(step_ms) // 2],
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "permuted": permuted, "sharded3d": sharded,
-            "gpu_launches": launches, "clocks": clocks}
+            "other_configs": other, "gpu_launches": launches, "clocks": clocks}
     if permuted:
         permuted["frac"] = evals_per_step / (permuted["ms_per_step"] * 1e-3) * FLOP_PER_EVAL / 1e12 / peak_tflops
     print(json.dumps(line))

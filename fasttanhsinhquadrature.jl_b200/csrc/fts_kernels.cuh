@@ -503,6 +503,37 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2)
         lo = a.low[b * a.bstride];
         hi = a.up[b * a.bstride];
     }
+    if constexpr (UsesExpTab<T, F>::value) {
+        // Bucket passes armed (uniform over the grid): a CTA whose warps ALL hand their integrals over leaves
+        // before the table fill — in a batch in arbitrary order that is every CTA, and this kernel shrinks to
+        // reading the parameters and writing the sort keys.  (Same classification as below; a zero-width
+        // integral is in no hurry: it goes through the regular path of whichever kernel gets it.)
+        if (a.sort_idx != nullptr) {
+            bool queued = false;
+            float key = 0.0f;
+            if (mine) {
+                const T half = num<T>::half();
+                T l2 = lo, h2 = hi;
+                bool n2 = false;
+                if (a.options & OPT_QUAD_EDGE) quad_edge_axis(l2, h2, n2);
+                const T bound = F::template exp_arg_bound<T>(fm::abs(half * (h2 + l2)) + fm::abs(half * (h2 - l2)), p);
+                const int q = __double2int_rd(fmin((double)bound, 1.0e7) * 8.0);
+                const unsigned m = __activemask();
+                queued = __reduce_max_sync(m, q) - __reduce_min_sync(m, q) > 2;
+                key = fminf(fmaxf((float)bound, 0.0f), 3.0e38f);
+            }
+            if (!__syncthreads_or(mine && !queued)) {
+                if (mine) {
+                    if ((threadIdx.x & 31) == 0) {
+                        a.sort_ctl[0] = 1;
+                        sort_mask(a)[b >> 5] = 1;
+                    }
+                    a.sort_idx[b] = __float_as_int(key);
+                }
+                return;
+            }
+        }
+    }
     family_tables_init<T, F>();  // before any thread leaves (contains a barrier)
     if (!mine) return;
     T dx, x0;

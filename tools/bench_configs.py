@@ -34,8 +34,14 @@ def best_of(fn, reps):
     return min(ts), out
 
 
+RECORDS = []  # bench.py calls the cases in-process and reads the records here instead of stdout
+QUIET = False
+
+
 def emit(**kw):
-    print(json.dumps(kw), flush=True)
+    RECORDS.append(kw)
+    if not QUIET:
+        print(json.dumps(kw), flush=True)
 
 
 def case_a(reps):
@@ -143,21 +149,27 @@ def case_cdev(reps):
     f = fts.builtin("c2_invsqrt_bmx_ymc")
     stream = torch.cuda.current_stream().cuda_stream
     for T, tt, rtol, ml in ((np.float64, torch.float64, 1e-10, 8), (np.float32, torch.float32, 1e-5, 6)):
+        ml = int(os.environ.get("FTS_BENCH_C_MAX_LEVELS", ml))  # 5: nothing can be queued, the queue pass is not launched
         cache = fts.adaptive_cache_2D_cmpl(T, max_levels=ml)
         lo, hi = torch.from_numpy(low.astype(T)).to(dev), torch.from_numpy(up.astype(T)).to(dev)
         val = torch.empty(n, dtype=tt, device=dev)
         lev = torch.empty(n, dtype=torch.int32, device=dev)
+        # K calls back to back per timed region, like the steps of bench.py: with ONE call between the events the
+        # 10 us the host spends between recording the first event and reaching cudaLaunchKernel (Python, ctypes,
+        # argument checks) are counted as device time of a 28 us kernel
+        K = int(os.environ.get("FTS_BENCH_C_CALLS", 10))
         ts = []
         for it in range(reps + 3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            api.adaptive_batch_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), bounds_stride=2, params=0, params_stride=0, rtol=rtol, atol=0.0,
-                                   max_levels=ml, batch=n, value=val.data_ptr(), levels=lev.data_ptr(), stream=stream, order="fast",
-                                   options=1)  # FTS_OPT_QUAD_EDGE_RULES
+            for _ in range(K):
+                api.adaptive_batch_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), bounds_stride=2, params=0, params_stride=0, rtol=rtol, atol=0.0,
+                                       max_levels=ml, batch=n, value=val.data_ptr(), levels=lev.data_ptr(), stream=stream, order="fast",
+                                       options=1)  # FTS_OPT_QUAD_EDGE_RULES
             e1.record()
             torch.cuda.synchronize()
             if it >= 3:
-                ts.append(e0.elapsed_time(e1))
+                ts.append(e0.elapsed_time(e1) / K)
         t = min(ts) * 1e-3
         levels = lev.cpu().numpy()
         evals = int(evals_for_level(2, levels).sum())
@@ -165,7 +177,7 @@ def case_cdev(reps):
              gevals_per_s=evals / t / 1e9, levels=np.bincount(levels).tolist(),
              max_rel_err_vs_exact=float(np.max(np.abs(val.cpu().numpy() - exact) / exact)),
              fp64_frac_nominal=(evals / t * 14.5 / 1e12 / FP64_PEAK) if T == np.float64 else None,
-             warp2d_levels=os.environ.get("FTS_B200_WARP2D_LEVELS", "default(5)"))
+             warp2d_levels=os.environ.get("FTS_B200_WARP2D_LEVELS", "default(5)"), calls_per_timed_region=K)
 
 
 def case_d(reps):
