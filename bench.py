@@ -533,7 +533,7 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_configs as bc
-            bc.QUIET, bc.FP64_PEAK = True, peak["tflops"]
+            bc.QUIET, bc.FP64_PEAK, bc.FP32_PEAK = True, peak["tflops"], fts.measure_fma_peak(np.float32, 8192)["tflops"]
             del bc.RECORDS[:]
             bc.case_cdev(10)
             bc.case_edev(5)

@@ -93,5 +93,9 @@ def test_our_arm_line():
     sh = d["sharded3d"]
     assert isinstance(sh, list) and {(x["family"], x["level"]) for x in sh} == {("exp_3d", 8), ("log_3d", 8), ("exp_3d", 9), ("log_3d", 9)}
     assert all(x["single"]["level_used"] == x["level"] and x["rel_err_vs_closed_form"] < 1e-11 for x in sh)
+    oc = d["other_configs"]
+    assert isinstance(oc, list) and {(x["case"], x.get("dtype") or x.get("family")) for x in oc} == {
+        ("C-device", "float64"), ("C-device", "float32"), ("E-device", "c_invsqrt"), ("E-device", "c_log_bmx")}
+    assert all(x["ms"] > 0 and x["gevals_per_s"] > 0 for x in oc) and all(x["max_rel_err_vs_exact"] < 1e-5 for x in oc if x["case"] == "C-device")
     assert d["gpu_launches"] >= d["steps"] and d["n_gpus"] == 1 and d["scaling"] == "weak"
     assert d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}

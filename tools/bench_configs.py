@@ -21,6 +21,7 @@ import fts_b200 as fts  # noqa: E402
 from fts_b200.api import evals_for_level  # noqa: E402
 
 FP64_PEAK = None
+FP32_PEAK = None
 
 
 def best_of(fn, reps):
@@ -177,6 +178,10 @@ def case_cdev(reps):
              gevals_per_s=evals / t / 1e9, levels=np.bincount(levels).tolist(),
              max_rel_err_vs_exact=float(np.max(np.abs(val.cpu().numpy() - exact) / exact)),
              fp64_frac_nominal=(evals / t * 14.5 / 1e12 / FP64_PEAK) if T == np.float64 else None,
+             # Float32: the same 14.5 flop/eval against the measured FFMA peak, and one MUFU.RSQ per evaluation against
+             # the SFU rate (16 per clock and SM: 148 x 16 x 1.965 GHz = 4.65 T/s)
+             fp32_frac_nominal=(evals / t * 14.5 / 1e12 / FP32_PEAK) if (T == np.float32 and FP32_PEAK) else None,
+             mufu_frac=(evals / t / 4.65e12) if T == np.float32 else None,
              warp2d_levels=os.environ.get("FTS_B200_WARP2D_LEVELS", "default(5)"), calls_per_timed_region=K)
 
 
@@ -314,14 +319,15 @@ def case_nd(reps):
 
 
 def main():
-    global FP64_PEAK
+    global FP64_PEAK, FP32_PEAK
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="A,C,D,E")
     ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
     fts.init(0)
     FP64_PEAK = fts.measure_fma_peak(np.float64, 8192)["tflops"]
-    emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=fts.measure_fma_peak(np.float32, 8192)["tflops"])
+    FP32_PEAK = fts.measure_fma_peak(np.float32, 8192)["tflops"]
+    emit(case="peak", fp64_tflops_measured=FP64_PEAK, fp32_tflops_measured=FP32_PEAK)
     for c in args.cases.split(","):
         {"A": case_a, "Apin": case_apin, "Adev": case_adev, "C": case_c, "Cdev": case_cdev, "D": case_d, "Dk": case_dk, "E": case_e, "Edev": case_edev, "ND": case_nd}[c](args.reps)
 
