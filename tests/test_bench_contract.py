@@ -88,7 +88,7 @@ def test_our_arm_line():
     assert r["traffic"] and 0 < r["frac_executed"] <= r["frac"] * 1.05 and 10 < r["fp64_instr_per_eval_executed"] < 25
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"] * 1.001 and e["matches_device_path_bitwise"]
     assert e["d2h_bytes_per_step"] == (1 << 20) * 12 and e["converged_from_flags"] == 1 << 20       # values AND flags come back
-    assert e["cold"]["value"] > 0 and 0 < e["frac_of_host_link"] < 1.5 and e["host_link_peak_gbs"] > 10
+    assert e["cold"]["value"] > 0 and 0 < e["frac_of_host_link"] < 3.0 and e["host_link_peak_gbs"] > 10
     assert d["permuted"]["value"] > 0 and 0 < d["permuted"]["frac"] < 1.2
     sh = d["sharded3d"]
     assert isinstance(sh, list) and {(x["family"], x["level"]) for x in sh} == {("exp_3d", 8), ("log_3d", 8), ("exp_3d", 9), ("log_3d", 9)}
