@@ -1397,7 +1397,10 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
             const int lw = max_levels < kWarpLevels ? max_levels : kWarpLevels;
             const int warps = fts::WARP2D_WARPS;
             const size_t ncap_w = (size_t)2 << lw;
-            const size_t smem_w = (size_t)warps * ((cmpl ? 9 : 5) * ncap_w * sizeof(T) + 2 * ncap_w * (cmpl ? 4 : 2) * sizeof(T) + 16);
+            // per warp (fts::warp2d_bytes): x-side records + y-side arrays of ncap + 1 entries, two raw node slices, two mbarriers
+            const size_t nc_w = ncap_w + 1, rec_w = sizeof(T) == 8 ? 6 : 8;
+            const size_t xy_w = nc_w * rec_w * sizeof(T) + ((5 * nc_w * sizeof(T) + 15) & ~(size_t)15), fb_w = (cmpl ? 9 : 5) * ncap_w * sizeof(T);
+            const size_t smem_w = (size_t)warps * ((xy_w > fb_w ? xy_w : fb_w) + 2 * ncap_w * (cmpl ? 4 : 2) * sizeof(T) + 16);
             int* queue = nullptr;
             if (int rc = tail_queue_for(s, (size_t)batch, &queue)) return rc;
             a.tail_count = queue;
@@ -1405,7 +1408,9 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
             a.tail_idx = queue + QUEUE_HEADER;
             a.group = 32;
             a.level = lw;
-            if (int rc = launch_raw(fn_warp, (unsigned)((batch + warps - 1) / warps), warps * 32, smem_w, &a, s)) return rc;
+            // a programmatic dependent of the previous kernel on the stream (it waits in `griddepcontrol.wait` before it
+            // touches global memory): in a loop of calls the set-up of this grid hides behind the previous call's queue pass
+            if (int rc = launch_dependent(fn_warp, (unsigned)((batch + warps - 1) / warps), warps * 32, smem_w, &a, s)) return rc;
             if (lw == max_levels) return FTS_OK;  // nothing can be queued
             // second pass: whole CTAs walk the queue of deeper integrals.  Two CTAs per SM: with an empty queue
             // (every integral converged in the warp pass) the launch is over in a couple of microseconds

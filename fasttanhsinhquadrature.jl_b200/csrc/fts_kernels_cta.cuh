@@ -236,8 +236,13 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ T axis2(const 
 {
     T f;
     if constexpr (CMPL) {
-        f = (F::template eval<T, true>(s.xp[i], s.y0, s.bx[i], s.ax[i], s.dy, s.dy, p) + F::template eval<T, true>(s.xm[i], s.y0, s.ax[i], s.bx[i], s.dy, s.dy, p)) +
-            (F::template eval<T, true>(s.x0, s.yp[i], s.dx, s.dx, s.dyc[i], s.cy[i], p) + F::template eval<T, true>(s.x0, s.ym[i], s.dx, s.dx, s.cy[i], s.dyc[i], p));
+        // the four evaluations side by side (same values as four F::eval calls: the batch evaluators are bit-identical)
+        const T xs[4] = {s.xp[i], s.xm[i], s.x0, s.x0}, ys[4] = {s.y0, s.y0, s.yp[i], s.ym[i]};
+        const T b_[4] = {s.bx[i], s.ax[i], s.dx, s.dx}, a_[4] = {s.ax[i], s.bx[i], s.dx, s.dx};
+        const T d_[4] = {s.dy, s.dy, s.dyc[i], s.cy[i]}, c_[4] = {s.dy, s.dy, s.cy[i], s.dyc[i]};
+        T v[4];
+        eval2dc_n<T, F, true, 4>(xs, ys, b_, a_, d_, c_, p, v);
+        f = (v[0] + v[1]) + (v[2] + v[3]);
     } else {
         f = (F::template eval<T, true>(s.xp[i], s.y0, p) + F::template eval<T, true>(s.xm[i], s.y0, p)) +
             (F::template eval<T, true>(s.x0, s.yp[i], p) + F::template eval<T, true>(s.x0, s.ym[i], p));
@@ -343,8 +348,9 @@ template <class T, bool CMPL> __device__ __forceinline__ Col2<T> load_col(const 
 // power of two >= 4: a lane owns a column j, keeps its y-side values in registers and walks down the rows —
 // the lanes of a row group read the same x-side entry (shared-memory broadcast), no flat-index decode per
 // cell.  Levels with fewer than 32 columns split the rows over 32/columns lane groups.
-template <class T, class F, bool CMPL> __device__ __forceinline__ T level_sum_2d_warp(const Sm2<T>& s, const T* p, int n, int lane)
+template <class T, class F, bool CMPL, int N = 0> __device__ __forceinline__ T level_sum_2d_warp(const Sm2<T>& s, const T* p, int n_runtime, int lane)
 {
+    const int n = N > 0 ? N : n_runtime;  // N > 0: the column/row-group arithmetic below folds into constants
     const XSide<T> x = make_xside<T, CMPL>(s);
     const unsigned nbytes = (unsigned)n * (unsigned)sizeof(T);
     T acc = num<T>::zero();
@@ -368,6 +374,23 @@ template <class T, class F, bool CMPL> __device__ __forceinline__ T level_sum_2d
     }
     for (int t = lane; t < (n >> 1); t += 32) acc = acc + axis2<T, F, CMPL>(s, p, t << 1);
     return acc;
+}
+
+// Four sums over the warp for the price of six shuffles: the lanes trade halves (xor 16, xor 8) before the plain
+// butterfly, so that every lane of the 8-lane class m = lane >> 3 ends up with the warp's total of S[m].
+template <class T> __device__ __forceinline__ T warp_reduce4(const T (&S)[4], int lane)
+{
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    T a0 = b4 ? S[2] : S[0], a1 = b4 ? S[3] : S[1];
+    const T o0 = b4 ? S[0] : S[2], o1 = b4 ? S[1] : S[3];
+    a0 = a0 + __shfl_xor_sync(0xffffffffu, o0, 16);
+    a1 = a1 + __shfl_xor_sync(0xffffffffu, o1, 16);
+    T k = b3 ? a1 : a0;
+    const T o = b3 ? a0 : a1;
+    k = k + __shfl_xor_sync(0xffffffffu, o, 8);
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) k = k + __shfl_xor_sync(0xffffffffu, k, off);
+    return k;
 }
 
 extern __shared__ __align__(16) unsigned char fts_dyn_smem[];
@@ -546,6 +569,314 @@ __device__ __forceinline__ void adaptive2d_group(const Args<T>& a, long long b, 
     }
 }
 
+// ---- the warp-shaped 2D adaptive path ---------------------------------------------------------------------------
+// One warp per integral, shallow levels (k_adaptive2d_warp).  Shared memory of a warp, NC = ncap + 1 entries
+// (the last entry is the CENTRE node, see warp_stage_centre):
+//   x-side RECORDS  [Δx·c, Δx·(1+x), x0+Δx·x, x0-Δx·x, w, pad]: the lanes that walk down a row read one record — a
+//                   broadcast, two or three vector loads off ONE address register, no per-array address arithmetic
+//   y-side ARRAYS   y0+Δy·x | y0-Δy·x | Δy·c | Δy·(1+x) | w: read once per column into registers
+//   two raw node slices (TMA destinations) and their two mbarriers.
+template <class T> struct WarpRec { static constexpr int ELEMS = sizeof(T) == 8 ? 6 : 8; };  // 48 / 32 bytes: 16-byte aligned records
+template <class T, bool CMPL> __host__ __device__ __forceinline__ size_t warp2d_bytes(int ncap)
+{
+    const size_t nc = (size_t)ncap + 1;
+    const size_t xy = nc * WarpRec<T>::ELEMS * sizeof(T) + ((5 * nc * sizeof(T) + 15) & ~(size_t)15);
+    const size_t fallback = (size_t)(CMPL ? 9 : 5) * ncap * sizeof(T);  // adaptive2d_group's arrays (batches with max_levels < 4)
+    return (xy > fallback ? xy : fallback) + 2 * (size_t)ncap * (CMPL ? sizeof(NodeC<T>) : sizeof(Node<T>)) + 16;
+}
+template <class T> struct WarpSm {
+    T* xrec;        // records
+    T* ycol;        // arrays, NC apart
+    int nc;
+    T dx, x0, dy, y0, w0;
+};
+__device__ __forceinline__ void lds_rec(unsigned addr, double& bx, double& ax, double& xp, double& xm)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(bx), "=d"(ax) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(xp), "=d"(xm) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void lds_rec(unsigned addr, float& bx, float& ax, float& xp, float& xm)
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bx), "=f"(ax), "=f"(xp), "=f"(xm) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ double lds_rec_w(unsigned addr, double)
+{
+    double w;
+    asm volatile("ld.shared.f64 %0, [%1+32];" : "=d"(w) : "r"(addr) : "memory");
+    return w;
+}
+__device__ __forceinline__ float lds_rec_w(unsigned addr, float)
+{
+    float w;
+    asm volatile("ld.shared.f32 %0, [%1+16];" : "=f"(w) : "r"(addr) : "memory");
+    return w;
+}
+// One node per lane: the hoist of adaptive.jl:570-580 (same expressions as sm2_stage) from a raw slice into
+// the records and arrays.
+template <class T, bool CMPL> __device__ __forceinline__ void warp_stage(const WarpSm<T>& s, const unsigned char* raw, int n, int lane)
+{
+    constexpr int RE = WarpRec<T>::ELEMS;
+    const T one = num<T>::one();
+    for (int i = lane; i < n; i += 32) {
+        T xi, wi, ci = one;
+        if constexpr (CMPL) {
+            const NodeC<T> nd = reinterpret_cast<const NodeC<T>*>(raw)[i];
+            xi = nd.x; wi = nd.w; ci = nd.c;
+        } else {
+            const Node<T> nd = reinterpret_cast<const Node<T>*>(raw)[i];
+            xi = nd.x; wi = nd.w;
+        }
+        T* r = s.xrec + (size_t)i * RE;
+        T* y = s.ycol + i;
+        r[2] = fm::fma(s.dx, xi, s.x0);
+        r[3] = fm::fma(-s.dx, xi, s.x0);
+        r[4] = wi;
+        y[0] = fm::fma(s.dy, xi, s.y0);
+        y[s.nc] = fm::fma(-s.dy, xi, s.y0);
+        y[4 * s.nc] = wi;
+        if constexpr (CMPL) {
+            r[0] = s.dx * ci;
+            r[1] = s.dx * (one + xi);
+            y[2 * s.nc] = s.dy * ci;
+            y[3 * s.nc] = s.dy * (one + xi);
+        }
+    }
+}
+// Entry ncap (the last one, whatever the level) is the CENTRE node with HALF its weight, staged once per integral: a
+// cell on the centre row or column has two pairs of coincident reflections, which the cell evaluator counts twice —
+// w_i (w0/2) (2 f + 2 f') is exactly the axis term w_i w0 (f + f') of adaptive.jl:204-206.
+template <class T, bool CMPL> __device__ __forceinline__ void warp_stage_centre(const WarpSm<T>& s)
+{
+    const int i = s.nc - 1;
+    T* r = s.xrec + (size_t)i * WarpRec<T>::ELEMS;
+    T* y = s.ycol + i;
+    const T wc = num<T>::half() * s.w0;
+    r[2] = s.x0; r[3] = s.x0; r[4] = wc;
+    y[0] = s.y0; y[s.nc] = s.y0; y[4 * s.nc] = wc;
+    if constexpr (CMPL) { r[0] = s.dx; r[1] = s.dx; y[2 * s.nc] = s.dy; y[3 * s.nc] = s.dy; }
+}
+template <class T, bool CMPL> __device__ __forceinline__ Col2<T> warp_col(const WarpSm<T>& s, int j)
+{
+    Col2<T> c;
+    const T* y = s.ycol + j;
+    c.yp = y[0]; c.ym = y[s.nc]; c.wj = y[4 * s.nc];
+    if constexpr (CMPL) { c.dyc = y[2 * s.nc]; c.cy = y[3 * s.nc]; }
+    else { c.dyc = num<T>::zero(); c.cy = num<T>::zero(); }
+    return c;
+}
+// acc + w_i w_j (f(x+,y+) + f(x-,y+) + f(x+,y-) + f(x-,y-)) for the record at shared address `rec`, the four
+// reflections evaluated side by side
+template <class T, class F, bool CMPL> __device__ __forceinline__ T warp_cell(unsigned rec, const T* p, const Col2<T>& c, T acc)
+{
+    T bx, ax, xp, xm, v[4];
+    lds_rec(rec, bx, ax, xp, xm);  // what the body does not read is dropped by ptxas
+    const T xs[4] = {xp, xm, xp, xm}, ys[4] = {c.yp, c.yp, c.ym, c.ym};
+    if constexpr (CMPL) {
+        const T b_[4] = {bx, ax, bx, ax}, a_[4] = {ax, bx, ax, bx}, d_[4] = {c.dyc, c.dyc, c.cy, c.cy}, c_[4] = {c.cy, c.cy, c.dyc, c.dyc};
+        eval2dc_n<T, F, true, 4>(xs, ys, b_, a_, d_, c_, p, v);
+    } else {
+        eval2d_n<T, F, true, 4, UsesExpTab<T, F>::value ? EXP_SMEM : 0>(xs, ys, p, v);
+    }
+    return fm::fma(lds_rec_w(rec, T()) * c.wj, (v[0] + v[1]) + (v[2] + v[3]), acc);
+}
+// Levels 0 .. 3 in ONE pass.  The level-3 slice (16 nodes per half-axis) holds the nodes of levels 0, 1, 2 at its
+// indices 7/15, 3/11, 1/5/9/13 (node t of level l is node 2t of level l + 1: t·h_l and 2t·h_(l+1) are the same
+// number, caches.jl:170-176).  At these sizes a level costs a warp far more in staging, reduction and stop test
+// (~430 instructions) than in cells (12 / 48 / 192 new cells over 32 lanes), so the warp evaluates the whole
+// 33 x 33 grid once, keeps the totals of the four levels apart, and then runs the stop tests of adaptive.jl:211-219
+// on them: value, error estimate and stop level are those of the level-by-level loop (an integral that stops at
+// level 1 or 2 has paid for cells it did not need — still fewer instructions than two or three separate levels).
+//   lane = 16 g + j owns column j and rows 8g .. 8g+7, walked in LEVEL order (7 | 3 | 1, 5 | 0, 2, 4, 6): the
+//   running sum after the rows of level m is the lane's share of the cells {level(i) <= m} of its column, which
+//   belong to total m iff m >= level(j).  Lanes of g = 0 also take the centre column at row j, lanes of g = 1 the
+//   centre row at column j: the axis terms, at the level of node j.
+template <class T, class F, bool CMPL> __device__ __forceinline__ void warp_levels_0_to_3(const WarpSm<T>& s, const T* p, int lane, T (&S)[4])
+{
+    constexpr unsigned RB = (unsigned)(WarpRec<T>::ELEMS * sizeof(T));
+    const unsigned x = smem_addr_pinned(s.xrec);
+    const int g = lane >> 4, j = lane & 15;
+    const int ctr = s.nc - 1;
+    const Col2<T> ce = warp_col<T, CMPL>(s, g ? j : ctr);
+    T acc = warp_cell<T, F, CMPL>(x + (unsigned)(g ? ctr : j) * RB, p, ce, num<T>::zero());
+    const Col2<T> c = warp_col<T, CMPL>(s, j);
+    const unsigned base = x + (unsigned)(8 * g) * RB;
+    acc = warp_cell<T, F, CMPL>(base + 7u * RB, p, c, acc);
+    const T P0 = acc;
+    acc = warp_cell<T, F, CMPL>(base + 3u * RB, p, c, acc);
+    const T P1 = acc;
+#pragma unroll 1
+    for (unsigned r = base + RB; r < base + 8u * RB; r += 4u * RB) acc = warp_cell<T, F, CMPL>(r, p, c, acc);
+    const T P2 = acc;
+#pragma unroll 1
+    for (unsigned r = base; r < base + 8u * RB; r += 2u * RB) acc = warp_cell<T, F, CMPL>(r, p, c, acc);
+    const int tz = __ffs(j + 1) - 1;      // node j is node (j + 1) h_3
+    const int lj = tz >= 3 ? 0 : 3 - tz;  // the level that brought it in
+    const T zero = num<T>::zero();
+    S[0] = lj <= 0 ? P0 : zero;
+    S[1] = lj <= 1 ? P1 : zero;
+    S[2] = lj <= 2 ? P2 : zero;
+    S[3] = acc;
+}
+// New cells of a level with n >= 32 nodes (0-based: rows i even -> every column, rows i odd -> even columns) and
+// its axis terms (centre column x new rows on lanes 0-15, centre row x new columns on lanes 16-31).  N > 0: n at
+// compile time, the column / row-group arithmetic folds into constants.
+template <class T, class F, bool CMPL, int N> __device__ __forceinline__ T warp_level_sum(const WarpSm<T>& s, const T* p, int n_runtime, int lane)
+{
+    constexpr unsigned RB = (unsigned)(WarpRec<T>::ELEMS * sizeof(T));
+    const int n = N > 0 ? N : n_runtime;
+    const unsigned x = smem_addr_pinned(s.xrec), xend = x + (unsigned)n * RB;
+    T acc = num<T>::zero();
+    for (int j = lane; j < n; j += 32) {  // even rows x all columns
+        const Col2<T> c = warp_col<T, CMPL>(s, j);
+#pragma unroll 1
+        for (unsigned r = x; r < xend; r += 2u * RB) acc = warp_cell<T, F, CMPL>(r, p, c, acc);
+    }
+    {   // odd rows x even columns: n/2 columns, two row groups when they are 16
+        const int half = n >> 1, cpl = half < 32 ? half : 32, sh = __ffs(cpl) - 1, groups = 32 >> sh;
+        const unsigned r0 = x + (unsigned)(1 + 2 * (lane >> sh)) * RB, step = (unsigned)(2 * groups) * RB;
+        for (int j = (lane & (cpl - 1)) << 1; j < n; j += 64) {
+            const Col2<T> c = warp_col<T, CMPL>(s, j);
+#pragma unroll 1
+            for (unsigned r = r0; r < xend; r += step) acc = warp_cell<T, F, CMPL>(r, p, c, acc);
+        }
+    }
+    const int g = lane >> 4;
+    for (int q = lane & 15; q < (n >> 1); q += 16) {  // axis terms of the new nodes 2q
+        const Col2<T> ce = warp_col<T, CMPL>(s, g ? 2 * q : s.nc - 1);
+        acc = warp_cell<T, F, CMPL>(x + (unsigned)(g ? s.nc - 1 : 2 * q) * RB, p, ce, acc);
+    }
+    return acc;
+}
+
+// adaptive_integrate_2D_avx (+ tensor-complement extension) by one warp, levels 0 .. level_cap with
+// 4 <= level_cap, level_cap <= a.max_levels (k_adaptive2d_warp sends shallower calls through adaptive2d_group)
+template <class T, class F> __device__ __forceinline__ void adaptive2d_warp(const Args<T>& a, long long b, int lane, unsigned char* mine, int ncap, int level_cap)
+{
+    constexpr bool CMPL = is_cmpl2d<F>::value;
+    constexpr int RE = WarpRec<T>::ELEMS;
+    WarpSm<T> s;
+    s.nc = ncap + 1;
+    s.xrec = reinterpret_cast<T*>(mine);
+    s.ycol = s.xrec + (size_t)s.nc * RE;
+    unsigned char* raw0 = mine + (size_t)s.nc * RE * sizeof(T) + ((5 * (size_t)s.nc * sizeof(T) + 15) & ~(size_t)15);
+    const size_t raw_bytes = (size_t)ncap * node_bytes<T, CMPL>();
+    // two mbarriers behind the raw slices; level l uses buffer and barrier l & 1, for the ((l - 3) >> 1)-th time
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(raw0 + 2 * raw_bytes), rawa = (unsigned)__cvta_generic_to_shared(raw0);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // node slice of `level` (n = 2^(level+1) records at offset n - 4) -> raw buffer level & 1, by the TMA unit
+    auto prefetch = [&](int level) {
+        if (lane != 0) return;
+        const int n = 2 << level;
+        const void* src = CMPL ? (const void*)(a.nodes_c + (n - 4)) : (const void*)(a.nodes + (n - 4));
+        const unsigned bytes = (unsigned)n * node_bytes<T, CMPL>(), bar = bar0 + 8u * (unsigned)(level & 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rawa + (unsigned)(level & 1) * (unsigned)raw_bytes),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    auto wait_slice = [&](int level) {
+        const unsigned bar = bar0 + 8u * (unsigned)(level & 1), parity = (unsigned)((level - 3) >> 1) & 1u;
+        unsigned done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        } while (!done);
+    };
+    prefetch(3);  // both slices are requested before the box is: one global-memory latency instead of two
+    prefetch(4);
+    T p[F::NP > 0 ? F::NP : 1];
+    load_params<F::NP>(p, a, b);
+    T lo[2], hi[2];
+    bool neg;
+    int flags;
+    if (!load_box<2>(a, b, lo, hi, neg, flags)) {
+        if (lane == 0) store_result(a, b, num<T>::zero(), num<T>::zero(), 0, FLAG_ZERO_WIDTH | FLAG_CONVERGED);
+        wait_slice(3);  // the requested slices land in this warp's shared memory: not before that may it be given up
+        wait_slice(4);
+        return;
+    }
+    const T half = num<T>::half();
+    s.dx = half * (hi[0] - lo[0]); s.x0 = half * (hi[0] + lo[0]);
+    s.dy = half * (hi[1] - lo[1]); s.y0 = half * (hi[1] + lo[1]);
+    s.w0 = num<T>::half_pi();
+    T h = a.tm * half;
+    // levels 0 .. 3 on the level-3 grid, their four stop tests afterwards
+    wait_slice(3);
+    warp_stage<T, CMPL>(s, raw0 + raw_bytes, 16, lane);
+    if (lane == 16) warp_stage_centre<T, CMPL>(s);
+    __syncwarp();
+    T old_res, err = num<T>::zero();
+    Comp<T> s_total;
+    {
+        T S[4];
+        warp_levels_0_to_3<T, F, CMPL>(s, p, lane, S);
+        T fc;
+        if constexpr (CMPL) fc = (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, s.dx, s.dx, s.dy, s.dy, p);
+        else fc = (s.w0 * s.w0) * F::template eval<T, true>(s.x0, s.y0, p);
+        const int m = lane >> 3;  // this lane's class holds the total of level m
+        const T tot = warp_reduce4<T>(S, lane) + fc;
+        T hm = h;
+        for (int q = 0; q < m; ++q) hm = hm * half;
+        const T res = s.dx * s.dy * (hm * hm) * tot;
+        const T prev = __shfl_up_sync(0xffffffffu, res, 8);
+        const T errm = fm::abs(res - prev);
+        const bool conv = m >= 1 && errm <= fm::err_target(res, a.rtol, a.atol) && may_stop(a.options, m, a.max_levels);
+        const unsigned stop = __ballot_sync(0xffffffffu, conv);
+        if (stop) {  // the first level whose test holds is where the level-by-level loop returns
+            wait_slice(4);  // the slice of level 4 has landed
+            if (lane == __ffs(stop) - 1) store_result(a, b, neg ? -res : res, errm, m, flags | FLAG_CONVERGED);
+            return;
+        }
+        s_total = comp_of(__shfl_sync(0xffffffffu, tot, 24));
+        old_res = __shfl_sync(0xffffffffu, res, 24);
+        h = __shfl_sync(0xffffffffu, hm, 24);
+    }
+    int level_used = 3;
+    int in_flight = 4;  // level whose slice has been requested but not yet consumed (0: none)
+    bool queued = false;
+    for (int level = 4; level <= a.max_levels; ++level) {
+        if (level > level_cap) {  // too deep for this warp's shared-memory slice: whole-CTA pass
+            if (lane == 0) a.tail_idx[atomicAdd(a.tail_count, 1)] = (int)b;
+            queued = true;
+            break;
+        }
+        h = h * half;
+        const int n = 2 << level;
+        __syncwarp();               // every lane is done with the previous level's records
+        wait_slice(level);          // the slice of this level has landed in shared memory
+        in_flight = 0;
+        warp_stage<T, CMPL>(s, raw0 + (size_t)(level & 1) * raw_bytes, n, lane);
+        __syncwarp();
+        if (level + 1 <= level_cap) {  // the other raw buffer was last read two levels ago: refill it during this level's evaluation
+            prefetch(level + 1);
+            in_flight = level + 1;
+        }
+        const T acc = n == 32 ? warp_level_sum<T, F, CMPL, 32>(s, p, 32, lane) : warp_level_sum<T, F, CMPL, 0>(s, p, n, lane);
+        const Comp<T> lv_sum = group_reduce<T, 32>(comp_of(acc), nullptr);
+        int done = 0;
+        if (lane == 0) {
+            s_total.merge(lv_sum);
+            const T new_res = s.dx * s.dy * (h * h) * s_total.value();
+            err = fm::abs(new_res - old_res);
+            old_res = new_res;
+            level_used = level;
+            const bool conv = err <= fm::err_target(new_res, a.rtol, a.atol) && may_stop(a.options, level, a.max_levels);
+            if (conv) flags |= FLAG_CONVERGED;
+            done = conv ? 1 : 0;
+        }
+        if (__shfl_sync(0xffffffffu, done, 0)) break;
+    }
+    if (in_flight) wait_slice(in_flight);  // a slice requested for a level that is never evaluated is still consumed
+    if (lane == 0 && !queued) {
+        if (!(flags & FLAG_CONVERGED) && a.max_levels > 0) flags |= FLAG_MAX_LEVELS;
+        store_result(a, b, neg ? -old_res : old_res, err, level_used, flags);
+    }
+}
+
 // Launch shapes of the cooperative 2D adaptive path:
 //   k_adaptive2d_warp  one WARP per integral up to level a.level (shallow integrals: 4 225 evaluations at
 //                      level 4 keep 32 lanes busy without any CTA barrier); CTAs of 4 warps and at most 72
@@ -557,17 +888,26 @@ constexpr int WARP2D_WARPS = 4;
 template <class T, class F> __global__ void __launch_bounds__(WARP2D_WARPS * 32, 7) k_adaptive2d_warp(const Args<T> a)
 {
     pdl_launch_dependents();     // the queue pass (k_adaptive2d_cta) may be set up behind this grid
-    family_tables_init<T, F>();  // barrier inside: before any early return
+    family_tables_init<T, F>();  // barrier inside: before any early return (constant tables only)
     constexpr bool CMPL = is_cmpl2d<F>::value;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * WARP2D_WARPS + warp;
     const int ncap = 2 << a.level;
-    unsigned char* mine = fts_dyn_smem + (size_t)warp * sm2_group_bytes<T, CMPL>(ncap);
+    unsigned char* mine = fts_dyn_smem + (size_t)warp * warp2d_bytes<T, CMPL>(ncap);
+    // This grid is itself launched as a programmatic dependent of whatever precedes it on the stream (in a loop of
+    // calls: the previous call's queue pass): its CTAs are set up behind that grid and touch global memory only
+    // from here on, after its completion and memory flush.
+    pdl_wait_primary();
+    if (b >= a.batch) return;
+    if (a.level >= 4) {
+        adaptive2d_warp<T, F>(a, b, lane, mine, ncap, a.level);
+        return;
+    }
+    // max_levels < 4 (or a lower cap asked for): the level-by-level group loop
     unsigned char* raw0 = mine + sm2_elems<T, CMPL>(ncap) * sizeof(T);
     NodePipe np;
     pipe_init(np, raw0 + 2 * (size_t)ncap * node_bytes<T, CMPL>(), raw0, raw0 + (size_t)ncap * node_bytes<T, CMPL>(), lane == 0);
     __syncwarp();
-    if (b >= a.batch) return;
     adaptive2d_group<T, F, 32>(a, b, lane, reinterpret_cast<T*>(mine), ncap, a.level, nullptr, nullptr, np);
 }
 
@@ -579,6 +919,7 @@ template <class T, class F> __global__ void __launch_bounds__(CTA_THREADS) k_ada
     if (a.tail_idx != nullptr) {
         // queue pass behind the warp pass: most calls leave nothing in the queue, and an empty pass should cost a
         // launch, not a table set-up (the count is uniform over the grid)
+        pdl_launch_dependents();  // the next call's warp pass may be set up behind this grid
         pdl_wait_primary();  // the warp pass has completed: the queue is final and visible
         if (*a.tail_count == 0) return;
     }

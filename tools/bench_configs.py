@@ -171,10 +171,45 @@ def case_cdev(reps):
             torch.cuda.synchronize()
             if it >= 3:
                 ts.append(e0.elapsed_time(e1) / K)
-        t = min(ts) * 1e-3
+        t_loop = min(ts) * 1e-3
+        # how long the HOST needs to queue one call (Python, ctypes, argument checks, two launches): when this is not
+        # below the device time, the loop above measures the host
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(20 * K):
+            api.adaptive_batch_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), bounds_stride=2, params=0, params_stride=0, rtol=rtol, atol=0.0,
+                                   max_levels=ml, batch=n, value=val.data_ptr(), levels=lev.data_ptr(), stream=stream, order="fast", options=1)
+        host_us = (time.perf_counter() - w0) / (20 * K) * 1e6
+        torch.cuda.synchronize()
+        # the same K calls captured into a CUDA graph (the entry point only queues work on the caller's stream) and
+        # replayed: device time per call without the host in the loop
+        t_graph = None
+        try:
+            side = torch.cuda.Stream()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+                cs = torch.cuda.current_stream().cuda_stream
+                for _ in range(K):
+                    api.adaptive_batch_dev(cache, f, low=lo.data_ptr(), up=hi.data_ptr(), bounds_stride=2, params=0, params_stride=0, rtol=rtol,
+                                           atol=0.0, max_levels=ml, batch=n, value=val.data_ptr(), levels=lev.data_ptr(), stream=cs, order="fast",
+                                           options=1)
+            tg = []
+            for it in range(reps + 3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    tg.append(e0.elapsed_time(e1) / K)
+            t_graph = min(tg) * 1e-3
+        except Exception as ex:  # noqa: BLE001 — the figure is optional, the reason is reported
+            print(f"[bench_configs] graph capture of config C failed: {ex}", file=sys.stderr)
+        t = t_graph if t_graph is not None else t_loop
         levels = lev.cpu().numpy()
         evals = int(evals_for_level(2, levels).sum())
-        emit(case="C-device", dtype=np.dtype(T).name, batch=n, ms=t * 1e3, ms_median=float(np.median(ts)), integrals_per_s=n / t,
+        emit(case="C-device", dtype=np.dtype(T).name, batch=n, ms=t * 1e3, ms_python_loop=t_loop * 1e3, ms_graph_replay=None if t_graph is None else t_graph * 1e3,
+             host_us_per_call=host_us, ms_median=float(np.median(ts)), integrals_per_s=n / t,
              gevals_per_s=evals / t / 1e9, levels=np.bincount(levels).tolist(),
              max_rel_err_vs_exact=float(np.max(np.abs(val.cpu().numpy() - exact) / exact)),
              fp64_frac_nominal=(evals / t * 14.5 / 1e12 / FP64_PEAK) if T == np.float64 else None,
