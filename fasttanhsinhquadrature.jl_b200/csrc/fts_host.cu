@@ -1448,6 +1448,7 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
     const void* fn_tail = (dim == 1 && max_levels > tail_level) ? integrand_kernel(f, c->dtype, KID_ADAPT_TAIL, fast) : nullptr;
     a.tail_level = -1;
     const void* fn_bucket = nullptr;
+    const void* fn_sort_all = nullptr;  // set: the whole batch goes through the bucket passes, k_adaptive1d_tpi is not launched
     if (fn_tail) {
         if (batch > 0x7fffffffLL) return set_error(FTS_ERR_INVALID_ARGUMENT, "batch too large for one launch");
         int* queue = nullptr;
@@ -1464,7 +1465,10 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
         // need (5 us of a 280 us call when they find nothing to do), so they are armed by feedback: every call detects
         // incoherent warps (k_adaptive1d_tpi) and the tail kernel leaves the finding in a pinned word; a call arms the
         // passes when the last finished call on its stream found such warps.  Results do not depend on the choice, bit
-        // for bit.  FTS_B200_BUCKET = 0: never armed, 2: always armed, 1 (default): by feedback.
+        // for bit.  The finding is a (sampled) COUNT of incoherent warps: when they were the majority, the whole batch
+        // goes through the passes (k_bucket_sort_all computes the keys itself) and k_adaptive1d_tpi — which would only
+        // read the parameters and write the keys, at the price of 8192 CTA launches per 2^20 integrals — is not launched.
+        // FTS_B200_BUCKET = 0: never armed, 2: always armed, 3: always the whole batch, 1 (default): by feedback.
         static const int bucket_mode = [] { const char* e = getenv("FTS_B200_BUCKET"); return e ? atoi(e) : 1; }();
         if (bucket_mode != 0 && !cmpl && c->dtype == FTS_F64 && batch >= 4LL * g_prop.multiProcessorCount * 256) {
             fn_bucket = integrand_kernel(f, c->dtype, KID_ADAPT_BUCKET, fast);
@@ -1477,12 +1481,22 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
                     cudaFuncAttributes fa;
                     cudaFuncGetAttributes(&fa, (const void*)&fts::k_bucket_sort<void>);
                     cudaFuncGetAttributes(&fa, fn_bucket);
+                    if (const void* fsa = integrand_kernel(f, c->dtype, KID_BUCKET_SORT_ALL, 0)) cudaFuncGetAttributes(&fa, fsa);
+                    else g_last_error.clear();
                     cudaGetLastError();
                     loaded.store(fn_bucket);
                 }
                 a.sort_fb = tq.fb_dev;
-                if (bucket_mode == 2 || *(volatile int*)tq.fb_host != 0) a.sort_idx = queue + QUEUE_HEADER + qcap;
-                else fn_bucket = nullptr;  // detect only
+                const long long found = *(volatile int*)tq.fb_host;  // ~ incoherent warps of the last finished call on this stream
+                if (bucket_mode >= 2 || found != 0) {
+                    a.sort_idx = queue + QUEUE_HEADER + qcap;
+                    if (bucket_mode == 3 || (bucket_mode == 1 && found * 64 >= batch)) {
+                        fn_sort_all = integrand_kernel(f, c->dtype, KID_BUCKET_SORT_ALL, 0);
+                        if (!fn_sort_all) g_last_error.clear();
+                    }
+                } else {
+                    fn_bucket = nullptr;  // detect only
+                }
             }
         }
     }
@@ -1501,14 +1515,20 @@ static int run_adaptive(fts_cache c, fts_integrand f, int order, int options, co
             }
         }
     }
-    if (int rc = launch(fn, threads, tpi_block(dim, c->dtype), &a, s)) return rc;
-    if (fn_bucket) {
-        const int* ctl = a.sort_ctl;
-        int* base = a.sort_idx;
-        long long nb = batch;
-        void* params[] = {(void*)&ctl, (void*)&base, (void*)&nb};
-        if (int rc = launch_dependent_params((const void*)&fts::k_bucket_sort<void>, (unsigned)((batch + fts::SORT_CHUNK - 1) / fts::SORT_CHUNK), 256, params, s)) return rc;
+    const unsigned chunks = (unsigned)((batch + fts::SORT_CHUNK - 1) / fts::SORT_CHUNK);
+    if (fn_sort_all) {
+        if (int rc = launch_dependent(fn_sort_all, chunks, 256, 0, &a, s)) return rc;
         if (int rc = launch_dependent(fn_bucket, (unsigned)g_prop.multiProcessorCount * 2, 256, 0, &a, s)) return rc;
+    } else {
+        if (int rc = launch(fn, threads, tpi_block(dim, c->dtype), &a, s)) return rc;
+        if (fn_bucket) {
+            const int* ctl = a.sort_ctl;
+            int* base = a.sort_idx;
+            long long nb = batch;
+            void* params[] = {(void*)&ctl, (void*)&base, (void*)&nb};
+            if (int rc = launch_dependent_params((const void*)&fts::k_bucket_sort<void>, chunks, 256, params, s)) return rc;
+            if (int rc = launch_dependent(fn_bucket, (unsigned)g_prop.multiProcessorCount * 2, 256, 0, &a, s)) return rc;
+        }
     }
     if (fn_tail) {
         const long long cap = (long long)g_prop.multiProcessorCount * 8;

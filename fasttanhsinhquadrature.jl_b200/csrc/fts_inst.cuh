@@ -59,8 +59,9 @@ struct Registrar {
     static const fts_host::KernelEntry k_bucket_entries_##FUNCTOR[] = {                                             \
         {FAM, FTS_F64, fts_host::KID_ADAPT_BUCKET, 0, FTS_KPTR(fts::k_adaptive1d_bucket<double, fts::FUNCTOR, false>)},    \
         {FAM, FTS_F64, fts_host::KID_ADAPT_BUCKET, 1, FTS_KPTR(fts::k_adaptive1d_bucket<double, fts::FUNCTOR, true>)},     \
+        {FAM, FTS_F64, fts_host::KID_BUCKET_SORT_ALL, 0, FTS_KPTR(fts::k_bucket_sort_all<double, fts::FUNCTOR>)},          \
     };                                                                                                               \
-    static fts_host::Registrar k_bucket_reg_##FUNCTOR(k_bucket_entries_##FUNCTOR, 2);
+    static fts_host::Registrar k_bucket_reg_##FUNCTOR(k_bucket_entries_##FUNCTOR, 3);
 
 // reference-order cooperative kernels of a 2D / 3D family (CTA per integral, ordered sum), f32 + f64
 #define FTS_REGISTER_ORD(FAM, FUNCTOR, ORD_K)                                                            \

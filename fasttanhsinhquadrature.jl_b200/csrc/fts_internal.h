@@ -26,7 +26,8 @@ enum KernelId : int {
     KID_ADAPT_BUCKET = 11, // k_adaptive1d_bucket             warp tasks over bound-ordered chunks (1D exp families, Float64, arbitrary parameter order)
     KID_ADAPT_GRP = 12,    // k_adaptive1d_grp                a group of 4 lanes per integral (Double64, 1D kinds); `fast` = 1: groups of 2
     KID_FIXED_ND = 13,     // k_fixed_nd                      generic n-D tensor product, fixed grid (NVRTC integrands of kind FTS_KIND_ND + D)
-    KID_COUNT = 14
+    KID_BUCKET_SORT_ALL = 14, // k_bucket_sort_all            keys + per-chunk ordering of a whole batch (first kernel of a call in arbitrary parameter order)
+    KID_COUNT = 15
 };
 
 struct KernelEntry {

@@ -133,7 +133,10 @@ template <class T, class F> struct UsesLogTab { static constexpr bool value = De
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-constexpr int SORT_CHUNK = 1024;  // integrals one CTA of k_bucket_sort orders
+#ifndef FTS_SORT_CHUNK
+#define FTS_SORT_CHUNK 1024
+#endif
+constexpr int SORT_CHUNK = FTS_SORT_CHUNK;  // integrals one CTA of k_bucket_sort orders (a multiple of 256)
 template <class T> __device__ __forceinline__ long long sort_padded(const Args<T>& a) { return (a.batch + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK; }
 template <class T> __device__ __forceinline__ int* sort_sorted(const Args<T>& a) { return a.sort_idx + sort_padded(a); }
 template <class T> __device__ __forceinline__ int* sort_mask(const Args<T>& a) { return a.sort_idx + 2 * sort_padded(a); }
@@ -526,6 +529,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2)
                 if (mine) {
                     if ((threadIdx.x & 31) == 0) {
                         a.sort_ctl[0] = 1;
+                        if (((b >> 5) & 7) == 0) atomicAdd(a.sort_ctl + 2, 8);  // one warp in 8 counts for 8
                         sort_mask(a)[b >> 5] = 1;
                     }
                     a.sort_idx[b] = __float_as_int(key);
@@ -554,7 +558,10 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2)
             const unsigned m = __activemask();
             const bool queued = __reduce_max_sync(m, q) - __reduce_min_sync(m, q) > 2;
             const bool leader = (int)(threadIdx.x & 31) == __ffs(m) - 1;
-            if (queued && leader) a.sort_ctl[0] = 1;
+            if (queued && leader) {
+                a.sort_ctl[0] = 1;
+                if (((b >> 5) & 7) == 0) atomicAdd(a.sort_ctl + 2, 8);  // sampled count of incoherent warps: the next call's choice of pass
+            }
             if (a.sort_idx != nullptr) {
                 if (leader) sort_mask(a)[b >> 5] = queued ? 1 : 0;
                 if (queued) {
@@ -878,22 +885,11 @@ template <class T, class F, bool FAST, bool CMPL> __device__ __forceinline__ voi
 // integral is computed by the same code as in the first kernel and writes to its own slot: results do not depend
 // on the order of the batch, bit for bit.  Integrals that are still unconverged at Args::tail_level join the deep
 // queue, which k_adaptive1d_tail (launched last) drains.
-template <class Tag> __global__ void __launch_bounds__(256) k_bucket_sort(const int* ctl, int* base, long long batch)
+// counting sort of one chunk: thread `tid` holds the keys v[k] of the chunk's integrals tid + 256 k (on[k]: takes part)
+__device__ __forceinline__ void bucket_sort_chunk(const float (&v)[SORT_CHUNK / 256], const bool (&on)[SORT_CHUNK / 256], int* sorted, long long c0, int* hist, int* sred)
 {
-    __shared__ int hist[SORT_CHUNK];
-    __shared__ int sred[12];
-    pdl_launch_dependents();
-    pdl_wait_primary();
-    if (ctl[0] == 0) return;            // no warp queued anything: uniform over the grid
-    const long long padded = (batch + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
-    const int* keys = base;
-    int* sorted = base + padded;
-    const int* mask = base + 2 * padded;
-    const int tid = threadIdx.x;
-    const long long c0 = (long long)blockIdx.x * SORT_CHUNK;
     constexpr int PER = SORT_CHUNK / 256;
-    float v[PER];
-    bool on[PER];
+    const int tid = threadIdx.x;
     if (tid == 0) {
         sred[8] = 0x7f7fffff;           // bits of the largest float
         sred[9] = 0;
@@ -903,15 +899,11 @@ template <class Tag> __global__ void __launch_bounds__(256) k_bucket_sort(const 
     __syncthreads();
     int lmin = 0x7f7fffff, lmax = 0;
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const long long i = c0 + tid + 256 * k;
-        on[k] = i < batch && mask[i >> 5] != 0;
-        v[k] = on[k] ? fminf(fmaxf(__int_as_float(keys[i]), 0.0f), 3.0e38f) : 0.0f;  // a lane that left before storing its key: any bucket will do
+    for (int k = 0; k < PER; ++k)
         if (on[k]) {
             lmin = min(lmin, __float_as_int(v[k]));  // the bits of a non-negative float are monotone in its value
             lmax = max(lmax, __float_as_int(v[k]));
         }
-    }
     lmin = __reduce_min_sync(0xffffffffu, lmin);
     lmax = __reduce_max_sync(0xffffffffu, lmax);
     if ((tid & 31) == 0) {
@@ -962,6 +954,78 @@ template <class Tag> __global__ void __launch_bounds__(256) k_bucket_sort(const 
     }
 }
 
+template <class Tag> __global__ void __launch_bounds__(256) k_bucket_sort(const int* ctl, int* base, long long batch)
+{
+    __shared__ int hist[SORT_CHUNK];
+    __shared__ int sred[12];
+    pdl_launch_dependents();
+    pdl_wait_primary();
+    if (ctl[0] == 0) return;            // no warp queued anything: uniform over the grid
+    const long long padded = (batch + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    const int* keys = base;
+    int* sorted = base + padded;
+    const int* mask = base + 2 * padded;
+    const int tid = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * SORT_CHUNK;
+    constexpr int PER = SORT_CHUNK / 256;
+    float v[PER];
+    bool on[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const long long i = c0 + tid + 256 * k;
+        on[k] = i < batch && mask[i >> 5] != 0;
+        v[k] = on[k] ? fminf(fmaxf(__int_as_float(keys[i]), 0.0f), 3.0e38f) : 0.0f;  // a lane that left before storing its key: any bucket will do
+    }
+    bucket_sort_chunk(v, on, sorted, c0, hist, sred);
+}
+
+// The whole batch through the bucket passes (a call whose predecessor on the stream found MOST warps incoherent): this
+// kernel is the call's first one — it computes the keys itself (same bound and same warp classification as
+// k_adaptive1d_tpi) and orders every integral of its chunk; k_adaptive1d_tpi, which would only have read the
+// parameters and written the keys, one 128-thread CTA per 128 integrals (8192 CTA launches for 2^20 integrals:
+// 26 us), is not launched at all.  It leaves the count of incoherent warps for the next call's choice.
+template <class T, class F> __global__ void __launch_bounds__(256) k_bucket_sort_all(const Args<T> a)
+{
+    __shared__ int hist[SORT_CHUNK];
+    __shared__ int sred[12];
+    pdl_launch_dependents();
+    pdl_wait_primary();
+    const int tid = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * SORT_CHUNK;
+    constexpr int PER = SORT_CHUNK / 256;
+    float v[PER];
+    bool on[PER];
+    int incoherent = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const long long i = c0 + tid + 256 * k;
+        on[k] = i < a.batch;
+        v[k] = 0.0f;
+        int q = 0;
+        if (on[k]) {
+            T p[F::NP > 0 ? F::NP : 1];
+            load_params<F::NP>(p, a, i);
+            const T half = num<T>::half();
+            T l2 = a.low[i * a.bstride], h2 = a.up[i * a.bstride];
+            bool n2 = false;
+            if (a.options & OPT_QUAD_EDGE) quad_edge_axis(l2, h2, n2);
+            const T bound = F::template exp_arg_bound<T>(fm::abs(half * (h2 + l2)) + fm::abs(half * (h2 - l2)), p);
+            q = __double2int_rd(fmin((double)bound, 1.0e7) * 8.0);
+            v[k] = fminf(fmaxf((float)bound, 0.0f), 3.0e38f);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, on[k]);
+        if (m) {
+            const int qmax = __reduce_max_sync(0xffffffffu, on[k] ? q : (int)0x80000000), qmin = __reduce_min_sync(0xffffffffu, on[k] ? q : 0x7fffffff);
+            if ((tid & 31) == 0 && qmax - qmin > 2) ++incoherent;
+        }
+    }
+    if ((tid & 31) == 0) {
+        if (incoherent) atomicAdd(a.sort_ctl + 2, incoherent);
+        if (tid == 0) a.sort_ctl[0] = 2;  // the bucket pass has work; 2: the count in sort_ctl[2] is exact (k_adaptive1d_tail)
+    }
+    bucket_sort_chunk(v, on, sort_sorted(a), c0, hist, sred);
+}
+
 template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_bucket(const Args<T> a)
 {
     pdl_launch_dependents();
@@ -969,7 +1033,7 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2)
     if (a.sort_ctl[0] == 0) return;     // uniform over the grid
     if constexpr (UsesExpTab<T, F>::value) {
         exp_tab8_init();
-        const int ntasks = (int)(sort_padded(a) / 32);
+        const int ntasks = (int)(sort_padded(a) / 32), nchunks = (int)(sort_padded(a) / SORT_CHUNK);
         const int* sorted = sort_sorted(a);
         const int lane = threadIdx.x & 31;
         // Task t = entries 32 t ... 32 t + 31 of the ordered chunks, claimed from a counter one at a time.  (Tried and
@@ -982,7 +1046,11 @@ template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2)
             if (lane == 0) t = atomicAdd(a.sort_ctl + 1, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= ntasks) break;
-            const int b = sorted[(long long)t * 32 + lane];
+            // claim order: the LAST 32 entries of every chunk first, the first ones last — the entries of a chunk are in
+            // ascending order of their bound, and for the exp families a larger bound means a deeper stop level, so
+            // the kernel ends on its cheapest tasks (a warp that draws a task near the end delays the grid by half as much)
+            const int slot = (SORT_CHUNK / 32 - 1) - t / nchunks, chunk = t - (t / nchunks) * nchunks;
+            const int b = sorted[(long long)chunk * SORT_CHUNK + slot * 32 + lane];
             if (b >= 0) {
                 T p[F::NP > 0 ? F::NP : 1];
                 load_params<F::NP>(p, a, b);
@@ -1023,8 +1091,9 @@ template <class T, class F, bool FAST, bool CMPL> __global__ void __launch_bound
         if (t == gridDim.x - 1) {
             *a.tail_count = 0;
             *a.ticket = 0u;
-            if (a.sort_fb) *a.sort_fb = a.sort_ctl[0];
-            if (a.sort_ctl) a.sort_ctl[0] = a.sort_ctl[1] = 0;
+            // ~ incoherent warps of this call: exact from k_bucket_sort_all, sampled (and never 0 when one was seen) from k_adaptive1d_tpi
+            if (a.sort_fb) *a.sort_fb = a.sort_ctl[0] == 2 ? a.sort_ctl[2] : (a.sort_ctl[0] ? (a.sort_ctl[2] > 0 ? a.sort_ctl[2] : 1) : 0);
+            if (a.sort_ctl) a.sort_ctl[0] = a.sort_ctl[1] = a.sort_ctl[2] = 0;
         }
     }
 }

@@ -12,7 +12,8 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_ROOT, "lib", "libfts_b200.so")
+# FTS_B200_LIB: another build of the same library (experiments with compile-time constants); default = the in-tree build
+LIB_PATH = os.environ.get("FTS_B200_LIB") or os.path.join(_ROOT, "lib", "libfts_b200.so")
 
 # status codes / enums (mirror of the header; tests/test_abi.py checks them against it)
 OK, ERR_INVALID_ARGUMENT, ERR_DIMENSION_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_NVRTC, ERR_NO_DEVICE, ERR_INTERNAL = range(8)

@@ -173,19 +173,31 @@ def test_bucket_pass_with_deep_integrals(gpu, oracle):
         return (v[:m].copy(), e[:m].copy(), lv[:m].copy(), fl[:m].copy()), gpu.launch_count() - before
 
     # the passes are armed by feedback from the previous call on the stream: the first shuffled call computes every
-    # integral where it lies and reports its incoherent warps, the second one goes through the passes
+    # integral where it lies and reports (a count of) its incoherent warps; when they were the majority the next call
+    # sends the whole batch through the passes (k_bucket_sort_all + bucket + tail: 3 launches, no k_adaptive1d_tpi),
+    # otherwise only the incoherent warps (tpi + sort + bucket + tail: 4 launches)
     a_coherent = _alpha(n)          # neighbours 2e-4 apart: no warp reports itself
     run(a_coherent)
-    _, k0 = run(a_coherent)
+    rc, k0 = run(a_coherent)
     r1, k1 = run(a_sorted[perm])
     r2, k2 = run(a_sorted[perm])
-    rs, _ = run(a_sorted)           # sorted, but neighbours at the upper end are several units apart: still through the passes
-    _, kc1 = run(a_coherent)
+    rs, ks = run(a_sorted)          # sorted, but above alpha ~ 160 (55 % of the warps) neighbours are more than 1/4 apart: still through the passes
+    _, kc1 = run(a_coherent)        # ... and so does the call after it, which finds every warp coherent
     _, kc2 = run(a_coherent)
-    assert (k0, k1, k2, kc1, kc2) == (2, 2, 4, 4, 2), (k0, k1, k2, kc1, kc2)  # tpi + tail | tpi + sort + bucket + tail
+    assert (k0, k1, k2, ks, kc1, kc2) == (2, 2, 3, 3, 3, 2), (k0, k1, k2, ks, kc1, kc2)
     for x1, x2, y in zip(r1, r2, rs):
         assert np.array_equal(x1, x2) and np.array_equal(x2, y[perm])
     assert r2[2].max() >= 10 and (r2[3] & L.FLAG_CONVERGED).all()
+    # a quarter of the batch in arbitrary order: only those warps go through the passes, the others compute in place
+    a_mix = a_coherent.copy()
+    a_mix[: n // 4] = a_sorted[perm][: n // 4]
+    _, km1 = run(a_mix)
+    rm, km2 = run(a_mix)
+    _, km3 = run(a_coherent)
+    _, km4 = run(a_coherent)
+    assert (km1, km2, km3, km4) == (2, 4, 4, 2), (km1, km2, km3, km4)
+    for xm, x2, xc in zip(rm, r2, rc):
+        assert np.array_equal(xm[: n // 4], x2[: n // 4]) and np.array_equal(xm[n // 4:], xc[n // 4:])
     # a small batch (below the size at which the passes exist) gives the same bits
     sub = np.random.default_rng(4).choice(n, 20000, replace=False)
     r3, k3 = run(a_sorted[perm][sub], 20000)
