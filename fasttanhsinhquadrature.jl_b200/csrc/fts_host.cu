@@ -694,14 +694,15 @@ template <class T> static T load_elem(const void* p) { T v; memcpy(&v, p, sizeof
 static double elem_hi(int dtype, const void* p) { return dtype == FTS_F32 ? (double)load_elem<float>(p) : load_elem<double>(p); }
 
 // dynamic shared memory a kernel may ask for: the opt-in maximum minus what the kernels declare
-// statically (reduction scratch, flags, the 4 KiB exp table region)
-static size_t dyn_smem_limit() { return (size_t)g_prop.sharedMemPerBlockOptin - 8192; }
+// statically (reduction scratch, flags, the 16 KiB exp table region / 3 KiB log table)
+constexpr size_t STATIC_SMEM_MAX = 20 * 1024;
+static size_t dyn_smem_limit() { return (size_t)g_prop.sharedMemPerBlockOptin - STATIC_SMEM_MAX; }
 
 // opt-in dynamic shared memory above 48 KiB: set once per kernel and size (the attribute call costs a
 // microsecond or two, which a 30 us launch notices)
 static int ensure_dyn_smem(const void* fn, size_t smem)
 {
-    if (smem <= 40 * 1024) return FTS_OK;
+    if (smem + STATIC_SMEM_MAX <= 48 * 1024) return FTS_OK;  // static + dynamic within the default limit: no opt-in needed
     if (smem > dyn_smem_limit())
         return set_error(FTS_ERR_UNSUPPORTED, "level needs " + std::to_string(smem) + " B of shared memory per CTA (max " +
                                                   std::to_string(dyn_smem_limit()) + ")");
