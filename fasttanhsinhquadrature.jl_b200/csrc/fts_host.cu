@@ -2,6 +2,7 @@
 // kernel registry and launch dispatch.  There is NO CPU fallback: every compute entry point
 // requires an sm_100 device and fails with FTS_ERR_NO_DEVICE / FTS_ERR_CUDA otherwise.
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1587,6 +1588,18 @@ extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int o
                                   int bounds_stride, const void* params, int params_stride, const void* rtol, const void* atol,
                                   int max_levels, int64_t batch, void* out_value, void* out_err, int32_t* out_levels, int32_t* out_flags)
 {
+    // FTS_B200_TRACE=1: host-side phases of this entry point (microseconds, averaged over 1000 calls, to stderr)
+    static const bool trace = [] { const char* e = getenv("FTS_B200_TRACE"); return e && atoi(e) != 0; }();
+    thread_local double tr_acc[4] = {0, 0, 0, 0};
+    thread_local int tr_n = 0;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto tr_mark = [&](int k, std::chrono::steady_clock::time_point& last) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        tr_acc[k] += std::chrono::duration<double, std::micro>(now - last).count();
+        last = now;
+    };
+    auto tr_last = tr0;
     if (int rc = check_adaptive(c, f, order, low, up, bounds_stride, params, params_stride, rtol, atol, max_levels, batch, out_value)) return rc;
     HostCtx* hc = nullptr;
     if (int rc = host_ctx(&hc)) return rc;
@@ -1623,6 +1636,7 @@ extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int o
     FTS_CUDA(resolve(S_ERR, out_err, (size_t)batch * es, es, true, true, oe));
     FTS_CUDA(resolve(S_LVL, out_levels, (size_t)batch * 4, 4, true, true, olv));
     FTS_CUDA(resolve(S_FLG, out_flags, (size_t)batch * 4, 4, true, true, ofl));
+    tr_mark(0, tr_last);  // checks + operand resolution
     Operand* ins[3] = {&ol, &ou, &op_};
     Operand* outs[4] = {&ov, &oe, &olv, &ofl};
     bool staged_in = false, staged_out = false;  // staged per-integral operands -> chunk pipeline
@@ -1660,9 +1674,17 @@ extern "C" int fts_adaptive_batch(fts_cache c, fts_integrand f, int order, int o
                 FTS_CUDA(cudaMemcpyAsync((char*)o->host + (size_t)b0 * o->elem, o->dev + (size_t)b0 * o->elem, (size_t)nbatch * o->elem,
                                          cudaMemcpyDeviceToHost, s));
     }
+    tr_mark(1, tr_last);  // staging copies queued, kernels launched
     if (nch > 1)
         for (int k = 0; k < 3; ++k) FTS_CUDA(cudaStreamSynchronize(g_pipe[k]));
     FTS_CUDA(cudaStreamSynchronize(g_stream));
+    tr_mark(2, tr_last);  // waiting for the device
+    if (trace && ++tr_n == 1000) {
+        fprintf(stderr, "[fts trace] fts_adaptive_batch, mean of 1000 calls: resolve %.2f us, queue %.2f us, wait %.2f us\n", tr_acc[0] / 1000, tr_acc[1] / 1000,
+                tr_acc[2] / 1000);
+        tr_n = 0;
+        tr_acc[0] = tr_acc[1] = tr_acc[2] = 0;
+    }
     return FTS_OK;
 }
 
