@@ -1,5 +1,5 @@
 #!/bin/bash
-# Fold the captures of one tools/gpu_round2_prof.sh call into profiles/ (kernel_profiles.json, ncu summaries, bench lines, launch list).
+# Fold the captures of one tools/gpu/profile_all.sh call into profiles/ (kernel_profiles.json, ncu summaries, bench lines, launch list).
 # usage: tools/fold_profiles.sh TAG   (reads gpurun_out/r2TAG_*)
 set -e
 TAG=$1
