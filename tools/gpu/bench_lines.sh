@@ -1,5 +1,5 @@
 #!/bin/bash
-# final bench lines on one GPU: bench.py both arms + tools/bench_configs.py.  usage: gpu_round2_b1.sh TAG
+# final bench lines on one GPU: bench.py both arms + tools/bench_configs.py.  usage: tools/gpu/bench_lines.sh TAG
 TAG=${1:-b1}
 set -x
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out

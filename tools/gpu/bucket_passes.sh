@@ -1,5 +1,5 @@
 #!/bin/bash
-# sort-all mode of the bucket passes: tests + bench (headline + permuted) per FTS_B200_BUCKET mode.  usage: gpu_round2_p2.sh TAG
+# sort-all mode of the bucket passes: tests + bench (headline + permuted) per FTS_B200_BUCKET mode.  usage: tools/gpu/bucket_passes.sh TAG
 TAG=${1:-p3}
 set -x
 cd "$GRAFT_REPO_ROOT"

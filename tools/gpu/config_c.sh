@@ -1,5 +1,5 @@
 #!/bin/bash
-# config C iteration: 2D tests, device-timed config C (loop + graph replay), ncu of the warp kernel.  usage: gpu_round2_c3.sh TAG
+# config C iteration: 2D tests, device-timed config C (loop + graph replay), ncu of the warp kernel.  usage: tools/gpu/config_c.sh TAG
 TAG=${1:-c3}
 set -x
 cd "$GRAFT_REPO_ROOT"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU check of the final state: bench.py both arms under torchrun + smoke.   usage: gpu_round2_multi2.sh N TAG
+# multi-GPU check of the final state: bench.py both arms under torchrun + smoke.   usage: tools/gpu/multi_gpu_bench.sh N TAG
 N=${1:-2}; TAG=${2:-m}
 set -x
 cd "$GRAFT_REPO_ROOT"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU call: bench.py both arms under torchrun, host-link probe, sharded 3D integral.   usage: gpu_round2_multi.sh N TAG
+# multi-GPU call: bench.py both arms under torchrun, host-link probe, sharded 3D integral.   usage: tools/gpu/multi_gpu_host_link.sh N TAG
 N=${1:-2}; TAG=${2:-m}
 set -x
 cd "$GRAFT_REPO_ROOT"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU profiling call: full tests, the bench line, and `ncu --set full` captures of the kernels recorded in
 # profiles/kernel_profiles.json (headline, config C warp kernel, log_3d level kernel) + the Double64 group kernel.
-# usage: gpu_round2_prof.sh TAG
+# usage: tools/gpu/profile_all.sh TAG
 TAG=${1:-prof}
 set -x
 cd "$GRAFT_REPO_ROOT"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# bucket-pass chunk size experiment: bench.py (headline + permuted) with SORT_CHUNK 1024 / 2048 / 4096 builds.  usage: gpu_round2_p1.sh TAG
+# bucket-pass chunk size experiment: bench.py (headline + permuted) with SORT_CHUNK 1024 / 2048 / 4096 builds.  usage: tools/gpu/sort_chunk_variants.sh TAG
 TAG=${1:-p1}
 set -x
 cd "$GRAFT_REPO_ROOT"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# full GPU suite only.  usage: gpu_round2_t1.sh TAG
+# full GPU suite only.  usage: tools/gpu/tests.sh TAG
 TAG=${1:-t1}
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=20 > gpurun_out/r2${TAG}_gputest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2${TAG}_gputest.log
