@@ -1582,32 +1582,42 @@ template <class T, class F, int D> __global__ void __launch_bounds__(CTA_THREADS
             }
         }
         const Comp<T> bsum = block_reduce(comp_of(acc), red);
-        if (tid == 0) {
-            a.block_partials[2 * blockIdx.x] = bsum.s;
-            a.block_partials[2 * blockIdx.x + 1] = bsum.c;
-            const unsigned int t = atom_add_acq_rel_gpu(a.ticket, 1u);  // releases the partials, acquires the other CTAs'
-            s_last = (t == nblk - 1) ? 1 : 0;
-        }
-        __syncthreads();
-        if (!s_last) {
-            if (!a.step_fused || level == level_hi || a.gen == nullptr) return;
-            // generation barrier: the last CTA publishes level + 1 (and the verdict) after the stop test of the level
-            if (tid == 0) s_gen = wait_generation(a.gen, a.gen_base + (unsigned int)(level + 1));
-            __syncthreads();
-            continue;
-        }
         Comp<T> tot;
-        for (int i = tid; i < (int)nblk; i += blockDim.x) {
-            Comp<T> o;
-            o.s = __ldcg(a.block_partials + 2 * i);
-            o.c = __ldcg(a.block_partials + 2 * i + 1);
-            tot.merge(o);
-        }
-        tot = block_reduce(tot, red);
-        if (tid == 0) {
-            a.partial_out[0] = tot.s;
-            a.partial_out[1] = tot.c;
-            *a.ticket = 0u;
+        if (nblk == 1) {
+            // a level that is ONE CTA small (levels 1 .. 4 of a 3D integral): its sum is the level's sum — no partials in
+            // global memory, no ticket, no read-back (three dependent global-memory round trips of a ~8 us level)
+            tot = bsum;  // valid in thread 0, the only one that uses it
+            if (tid == 0) {
+                a.partial_out[0] = tot.s;
+                a.partial_out[1] = tot.c;
+            }
+        } else {
+            if (tid == 0) {
+                a.block_partials[2 * blockIdx.x] = bsum.s;
+                a.block_partials[2 * blockIdx.x + 1] = bsum.c;
+                const unsigned int t = atom_add_acq_rel_gpu(a.ticket, 1u);  // releases the partials, acquires the other CTAs'
+                s_last = (t == nblk - 1) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_last) {
+                if (!a.step_fused || level == level_hi || a.gen == nullptr) return;
+                // generation barrier: the last CTA publishes level + 1 (and the verdict) after the stop test of the level
+                if (tid == 0) s_gen = wait_generation(a.gen, a.gen_base + (unsigned int)(level + 1));
+                __syncthreads();
+                continue;
+            }
+            for (int i = tid; i < (int)nblk; i += blockDim.x) {
+                Comp<T> o;
+                o.s = __ldcg(a.block_partials + 2 * i);
+                o.c = __ldcg(a.block_partials + 2 * i + 1);
+                tot.merge(o);
+            }
+            tot = block_reduce(tot, red);
+            if (tid == 0) {
+                a.partial_out[0] = tot.s;
+                a.partial_out[1] = tot.c;
+                *a.ticket = 0u;
+            }
         }
         const bool exchange = a.peer_mail[0] != nullptr && sharded;
         const int slot_row = a.mail_slot + (level - a.level);
