@@ -526,6 +526,52 @@ def test_adaptive_2d_warp_per_integral_and_queue(gpu, oracle):
     assert rm.converged.all() and rel(rm.value[keep], ex[keep]).max() < 1e-9
 
 
+def test_adaptive_2d_warp_kernel_stop_levels(gpu, oracle):
+    """The warp-per-integral kernel evaluates levels 0 .. 3 in ONE pass and runs their stop tests afterwards: value,
+    error estimate and stop level must be those of the level-by-level loop whichever level the tolerance stops at
+    (1, 2, 3: inside the fused pass; 4: the level after it; 5+: queue pass), with max_levels below 4 (the
+    level-by-level fallback of the same kernel), with max_levels = 4 (nothing can be queued), under forced depth, and
+    for the complement family and Float32."""
+    oc = oracle.cache_tensor("f64", 2, 8)
+    cache = gpu.adaptive_cache_2D(np.float64, max_levels=8)
+    n = 8 * gpu.device_info()["sm_count"] + 64
+    rng = np.random.default_rng(17)
+    low = np.stack([-1 - rng.random(n), -1 - rng.random(n)], axis=1)
+    up = np.stack([1 + rng.random(n), 0.5 + rng.random(n)], axis=1)
+    f, fam = gpu.builtin("exp_2d"), F["F2_EXP"]
+    seen = set()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for rtol, ml in ((3e-1, 8), (1e-2, 8), (1e-4, 8), (1e-7, 8), (1e-11, 8), (1e-14, 8), (1e-7, 2), (1e-7, 3), (1e-9, 4), (1e-13, 4)):
+            r = gpu.adaptive_integrate_2D_avx(np.float64, f, low, up, rtol=rtol, max_levels=ml, cache=cache, full_output=True)
+            for i in (0, 1, n // 2, n - 1):
+                ref = oracle.adaptive_nd("f64x", 2, fam, None, low[i], up[i], rtol, 0.0, ml, oc)
+                assert r.levels[i] == ref.level and rel(r.value[i], ref.value) <= RTOL64, (rtol, ml, i, r.levels[i], ref.level)
+                assert bool(r.converged[i]) == bool(ref.converged)
+                if ref.level > 0:
+                    assert abs(r.err[i] - ref.err) <= 1e-12 * max(abs(ref.value), 1e-300) + 4 * RTOL64 * abs(ref.value)
+            seen |= set(np.unique(r.levels).tolist())
+        assert {1, 2, 3, 4, 5} <= seen, seen
+        # forced depth: no stop test may end the integral before max_levels
+        rf = gpu.adaptive_integrate_2D_avx(np.float64, f, low, up, rtol=1e-2, max_levels=4, cache=cache, full_output=True, force_depth=True)
+        rq = gpu.adaptive_integrate_2D_avx(np.float64, f, low, up, rtol=1e-2, max_levels=6, cache=cache, full_output=True, force_depth=True)
+    assert (rf.levels == 4).all() and (rq.levels == 6).all()
+    exact = (np.exp(up[:, 0]) - np.exp(low[:, 0])) * (np.exp(up[:, 1]) - np.exp(low[:, 1]))
+    assert rel(rf.value, exact).max() < 1e-9 and rel(rq.value, exact).max() < 1e-12
+    # complement family (axis terms through the centre entry with complement distances) and Float32
+    occ = oracle.cache_tensor_cmpl("f64", 8)
+    cc = gpu.adaptive_cache_2D_cmpl(np.float64, max_levels=8)
+    fc = gpu.builtin("c2_invsqrt_bmx_ymc")
+    for rtol in (1e-2, 1e-4, 1e-6, 1e-10):
+        rc = gpu.quad_cmpl(fc, low, up, rtol=rtol, max_levels=8, cache=cc, order="fast", full_output=True)
+        for i in (0, n // 3, n - 1):
+            ref = oracle.adaptive2d_cmpl("f64x", F["C2_INVSQRT_BMX_YMC"], None, low[i], up[i], rtol, 0.0, 8, occ)
+            assert rc.levels[i] == ref.level and rel(rc.value[i], ref.value) <= RTOL64, (rtol, i, rc.levels[i], ref.level)
+    c32 = gpu.adaptive_cache_2D(np.float32, max_levels=6)
+    r32 = gpu.adaptive_integrate_2D_avx(np.float32, f, low.astype(np.float32), up.astype(np.float32), rtol=1e-4, max_levels=6, cache=c32, full_output=True)
+    assert r32.converged.all() and rel(r32.value, exact).max() < 2e-4
+
+
 def test_reference_order_cooperative_kernels_match_thread_per_integral(gpu, oracle):
     """Small 2D/3D batches in reference order run one CTA per integral (terms evaluated in parallel,
     added in the reference's loop order); batches of >= 64 x SMs integrals run one thread per
