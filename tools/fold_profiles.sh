@@ -17,6 +17,10 @@ python tools/ncu_summary.py ${G}_headline.ncu-rep profiles/r2_adaptive1d_tpi_hea
 python tools/ncu_summary.py ${G}_configc.ncu-rep profiles/r2_config_c_warp_kernel_ncu_full.md "config C (4096 boxes, FP64): k_adaptive2d_warp + queue pass, round 2 call $TAG"
 python tools/ncu_summary.py ${G}_log3d.ncu-rep profiles/r2_level_grid_log3d_table_log_ncu_full.md "k_level_grid<double,F3Log,3> level 8 (table-driven log), round 2 call $TAG"
 python tools/ncu_summary.py ${G}_dd_grp.ncu-rep profiles/r2_adaptive1d_grp_dd_ncu_full.md "config E: k_adaptive1d_grp<dd,C1InvSqrt> (Double64, 4 lanes per integral), round 2 call $TAG"
+if [ -f ${G}_bucket.ncu-rep ]; then
+  python tools/ncu_summary.py ${G}_bucket.ncu-rep profiles/r2_adaptive1d_bucket_ncu_full.md "config B with shuffled parameters: k_bucket_sort_all + k_adaptive1d_bucket, round 2 call $TAG"
+  cp ${G}_launches_permuted.csv profiles/r2${TAG}_bench_launches_permuted.csv
+fi
 cp ${G}_bench.json profiles/r2${TAG}_bench_1gpu.json
 cp ${G}_bench_ref.json profiles/r2${TAG}_bench_ref_1gpu.json
 cp ${G}_configs.jsonl profiles/r2${TAG}_configs_c_d_e_nd.jsonl

@@ -20,7 +20,10 @@ D="python tools/bench_configs.py --cases Dk --reps 1"
 FTS_BENCH_DK=log_3d:8 timeout 200 $D > gpurun_out/r2${TAG}_plain_d.log 2>&1 && FTS_BENCH_DK=log_3d:8 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_level_grid -s 2 -c 1 -f -o gpurun_out/r2${TAG}_log3d $D > gpurun_out/r2${TAG}_ncu_d.log 2>&1
 Ee="python tools/bench_configs.py --cases Edev --reps 1"
 timeout 200 $Ee > gpurun_out/r2${TAG}_plain_e.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_adaptive1d_grp -s 2 -c 1 -f -o gpurun_out/r2${TAG}_dd_grp $Ee > gpurun_out/r2${TAG}_ncu_e.log 2>&1
-tail -2 gpurun_out/r2${TAG}_ncu_b.log gpurun_out/r2${TAG}_ncu_c.log gpurun_out/r2${TAG}_ncu_d.log gpurun_out/r2${TAG}_ncu_e.log
+P="python bench.py --permute --steps 2 --warmup 3 --no-cpu-baseline --no-sharded3d --no-permuted --no-host-link --no-other-configs"
+timeout 200 $P > gpurun_out/r2${TAG}_plain_p.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_adaptive1d_bucket|k_bucket_sort_all" -s 4 -c 2 -f -o gpurun_out/r2${TAG}_bucket $P > gpurun_out/r2${TAG}_ncu_p.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_adaptive1d|k_bucket" -c 24 --csv --log-file gpurun_out/r2${TAG}_launches_permuted.csv $P > gpurun_out/r2${TAG}_ncu_pl.log 2>&1
+tail -n 2 gpurun_out/r2${TAG}_ncu_b.log gpurun_out/r2${TAG}_ncu_p.log gpurun_out/r2${TAG}_ncu_c.log gpurun_out/r2${TAG}_ncu_d.log gpurun_out/r2${TAG}_ncu_e.log
 python - <<P
 import json
 d = json.loads([l for l in open("gpurun_out/r2${TAG}_bench.json") if l.startswith("{")][-1])
