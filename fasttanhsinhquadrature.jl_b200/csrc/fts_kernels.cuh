@@ -28,6 +28,11 @@ enum : int { FLAG_CONVERGED = 1, FLAG_MAX_LEVELS = 2, FLAG_ZERO_WIDTH = 4, FLAG_
 #ifndef FTS_TPI_PAIRS
 #define FTS_TPI_PAIRS 4
 #endif
+// trips of that loop per branch in the kernels whose evaluation is short (table exp without range test: EXP_SAFE):
+// loop control and the constant reloads are 11 of 167 instructions per trip there (config B 0.2682 -> 0.2659 ms)
+#ifndef FTS_TPI_UNROLL
+#define FTS_TPI_UNROLL 4
+#endif
 constexpr int TPI_PAIRS = FTS_TPI_PAIRS;  // node pairs per loop trip of the thread-per-integral 1D kernels (levels >= 2)
 
 template <class T> struct Node { T x, w; };             // 1D / tensor tables, interleaved
@@ -441,8 +446,7 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
             s_new = muladd<T, FAST>(n1.w, fs[2] + fs[3], s_new);
         } else {
             constexpr int PAIRS = TPI_PAIRS;
-#pragma unroll 1
-            for (int i = 0; i < n; i += PAIRS) {
+            auto trip = [&](int i) {
                 T xs[2 * PAIRS], ws[PAIRS], fs[2 * PAIRS];
 #pragma unroll
                 for (int k = 0; k < PAIRS; ++k) {
@@ -455,6 +459,17 @@ __device__ __forceinline__ void adaptive1d_tpi_levels(const Args<T>& a, long lon
                 eval1d_n<T, F, FAST, 2 * PAIRS, MODE>(xs, p, fs);
 #pragma unroll
                 for (int k = 0; k < PAIRS; ++k) s_new = muladd<T, FAST>(ws[k], fs[2 * k] + fs[2 * k + 1], s_new);
+            };
+            constexpr int UNR = (MODE & EXP_SAFE) ? FTS_TPI_UNROLL : 1;
+            if (UNR > 1 && n >= UNR * PAIRS) {
+#pragma unroll 1
+                for (int i = 0; i < n; i += UNR * PAIRS) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) trip(i + u * PAIRS);
+                }
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < n; i += PAIRS) trip(i);
             }
         }
         s_total = s_total + s_new;
@@ -494,7 +509,11 @@ template <class T, class F> __device__ __forceinline__ bool tpi_finish_prologue(
     return true;
 }
 
-template <class T, class F, bool FAST> __global__ void __launch_bounds__(256, 2) k_adaptive1d_tpi(const Args<T> a)
+#ifndef FTS_TPI_LB_THREADS
+#define FTS_TPI_LB_THREADS 256
+#define FTS_TPI_LB_BLOCKS 2
+#endif
+template <class T, class F, bool FAST> __global__ void __launch_bounds__(FTS_TPI_LB_THREADS, FTS_TPI_LB_BLOCKS) k_adaptive1d_tpi(const Args<T> a)
 {
     pdl_launch_dependents();     // the kernels behind this one may be set up behind this grid's last wave
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
