@@ -344,6 +344,56 @@ def test_deep_level_tail_keeps_reference_order(gpu, oracle):
     assert np.array_equal(r32.levels, ref32["level"]) and rel(r32.value, ref32["value"]).max() <= 1e-6
 
 
+def test_edge_batches_empty_ragged_and_nonfinite(gpu, oracle):
+    """Edge cases of a batch: empty, one element, sizes that are no multiple of the warp / CTA / warps-per-CTA
+    counts, NaN and Inf parameters (the reference's loop runs such an integral to max_levels: `err <= tol` is false
+    for NaN, adaptive.jl:60-69), max_levels = 0 (level-0 estimate, no warning: adaptive.jl:70).  Value, level and
+    convergence flag against the oracle's loop over the same inputs."""
+    oc = oracle.cache1d("f64", 12)
+    cache = gpu.adaptive_cache_1D(np.float64, max_levels=12)
+    f = gpu.builtin("runge")
+    r0 = gpu.quad(f, -1.0, 1.0, rtol=1e-10, max_levels=12, cache=cache, params=np.zeros(0), order="reference", full_output=True)
+    assert r0.value.shape == (0,) and r0.levels.shape == (0,) and r0.flags.shape == (0,)
+    assert gpu.adaptive_integrate_1D_avx(np.float64, f, -1.0, 1.0, rtol=1e-10, max_levels=12, cache=cache, params=np.zeros(0)).shape == (0,)
+    rng = np.random.default_rng(17)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n in (1, 2, 31, 32, 33, 127, 129, 1023, 1025, 4099):
+            a = 1.0 + 99.0 * rng.random(n)
+            if n >= 31:
+                a[n // 2] = np.nan          # runs to max_levels, NaN out, not converged
+                a[n - 1] = np.inf           # 1/(1 + inf * x^2): 0 off the centre, inf * 0 = NaN at it
+                a[0] = 1e7                  # leaves through the deep queue at max_levels (not converged)
+            lo, up = -1.0 - rng.random(n), 1.0 + rng.random(n)
+            r = gpu.quad(f, lo, up, rtol=1e-10, max_levels=12, cache=cache, params=a, order="reference", full_output=True)
+            ref = oracle.batch_adaptive1d("f64", F["F1_RUNGE"], a, lo, up, 1e-10, 0.0, 12, oc)
+            assert np.array_equal(r.levels, ref["level"]) and np.array_equal(r.converged, ref["converged"]), n
+            assert np.array_equal(np.isnan(r.value), np.isnan(ref["value"])), n
+            ok = ~np.isnan(ref["value"])
+            assert rel(r.value[ok], ref["value"][ok]).max(initial=0.0) <= 1e-15, n
+            if n >= 31:
+                assert np.isnan(r.value[n // 2]) and r.levels[n // 2] == 12 and (r.flags[n // 2] & gpu.FLAG_MAX_LEVELS)
+            # the cooperative order on the same ragged batch (one CTA per integral / thread per integral by size)
+            rf = gpu.adaptive_integrate_1D_avx(np.float64, f, lo, up, rtol=1e-10, max_levels=12, cache=cache, params=a, full_output=True)
+            assert np.array_equal(np.isnan(rf.value), np.isnan(ref["value"])) and rel(rf.value[ok & ref["converged"]], ref["value"][ok & ref["converged"]]).max(initial=0.0) <= 1e-9, n
+        # max_levels = 0: the level-0 estimate (5 evaluations), flagged neither converged nor max_levels
+        a = 1.0 + 99.0 * rng.random(77)
+        r = gpu.quad(f, -1.0, 1.0, rtol=1e-10, max_levels=0, cache=cache, params=a, order="reference", full_output=True)
+        ref = oracle.batch_adaptive1d("f64", F["F1_RUNGE"], a, [-1.0], [1.0], 1e-10, 0.0, 0, oc)
+        assert (r.levels == 0).all() and np.array_equal(r.levels, ref["level"]) and rel(r.value, ref["value"]).max() <= 1e-15
+        assert not (r.flags & gpu.FLAG_MAX_LEVELS).any()
+    # 2D: a batch that is no multiple of the warps per CTA of the warp-per-integral kernel, and tiny batches
+    oc2 = oracle.cache_tensor("f64", 2, 6)
+    c2 = gpu.adaptive_cache_2D(np.float64, max_levels=6)
+    for n in (1, 3, 8 * gpu.device_info()["sm_count"] + 41):
+        low = np.stack([-1 - rng.random(n), -1 - rng.random(n)], axis=1); up = np.stack([1 + rng.random(n), 0.5 + rng.random(n)], axis=1)
+        r = gpu.adaptive_integrate_2D_avx(np.float64, gpu.builtin("exp_2d"), low, up, rtol=1e-9, max_levels=6, cache=c2, full_output=True)
+        assert r.converged.all()
+        for i in sorted({0, n // 2, n - 1}):
+            refx = oracle.adaptive_nd("f64x", 2, F["F2_EXP"], None, low[i], up[i], 1e-9, 0.0, 6, oc2)
+            assert r.levels[i] == refx.level and rel(r.value[i], refx.value) <= RTOL64, (n, i)
+
+
 # ------------------------------------------------------------------ fixed grids ---------------
 def test_fixed_grid_1d_batch(gpu, oracle):
     """config A: integrate1D[_avx] of exp on [0, b_k], N in {80, 256, 1024}"""
