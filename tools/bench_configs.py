@@ -143,7 +143,7 @@ def case_cdev(reps):
     from fts_b200 import api
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
-    n = 4096
+    n = int(os.environ.get("FTS_BENCH_C_BATCH", 4096))  # BASELINE: 4096 (one wave of warps); larger batches show the kernel's throughput
     low = np.stack([-3 + 2 * rng.random(n), -3 + 2 * rng.random(n)], axis=1)
     up = np.stack([1 + 2 * rng.random(n), 1 + 2 * rng.random(n)], axis=1)
     exact = 4 * np.sqrt((up[:, 0] - low[:, 0]) * (up[:, 1] - low[:, 1]))
