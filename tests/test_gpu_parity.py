@@ -492,9 +492,9 @@ def test_config_c_2d_complement(gpu, oracle):
     r = gpu.quad_cmpl(f, low, up, rtol=1e-10, max_levels=8, cache=cache, order="fast", full_output=True)
     assert r.converged.all() and rel(r.value, exact).max() < 1e-9
     oc = oracle.cache_tensor_cmpl("f64", 8)
-    for i in range(0, n, 512):
+    for i in range(n):  # every one of the 4096 boxes against the exactly-summed oracle (17 M evaluations)
         ref = oracle.adaptive2d_cmpl("f64x", F["C2_INVSQRT_BMX_YMC"], None, low[i], up[i], 1e-10, 0.0, 8, oc)
-        assert r.levels[i] == ref.level and rel(r.value[i], ref.value) <= RTOL64
+        assert r.levels[i] == ref.level and rel(r.value[i], ref.value) <= RTOL64, i
     rr = gpu.quad_cmpl(f, low[:64], up[:64], rtol=1e-10, max_levels=8, cache=cache, order="reference", full_output=True)
     for i in range(0, 64, 16):
         ref = oracle.adaptive2d_cmpl("f64", F["C2_INVSQRT_BMX_YMC"], None, low[i], up[i], 1e-10, 0.0, 8, oc)
@@ -502,6 +502,14 @@ def test_config_c_2d_complement(gpu, oracle):
     c32 = gpu.adaptive_cache_2D_cmpl(np.float32, max_levels=6)
     r32 = gpu.quad_cmpl(f, low.astype(np.float32), up.astype(np.float32), rtol=1e-5, max_levels=6, cache=c32, order="fast", full_output=True)
     assert r32.value.dtype == np.float32 and rel(r32.value, exact).max() < 5e-5
+    oc32 = oracle.cache_tensor_cmpl("f32", 6)
+    lo32, up32 = low.astype(np.float32), up.astype(np.float32)
+    same = 0
+    for i in range(n):  # Float32: all 4096 against the exactly-summed Float32 oracle (tolerance 1e-5, BASELINE north_star)
+        ref = oracle.adaptive2d_cmpl("f32x", F["C2_INVSQRT_BMX_YMC"], None, lo32[i], up32[i], 1e-5, 0.0, 6, oc32)
+        same += int(r32.levels[i] == ref.level)
+        assert abs(float(r32.value[i]) - ref.value) <= 1e-5 * abs(ref.value), i
+    assert same >= 0.99 * n  # rsqrtf (2 ulp) against sqrtf + division can move a borderline stop test by one level
 
 
 # ------------------------------------------------------------------ adaptive 2D / 3D ----------
