@@ -93,3 +93,106 @@ def test_product_never_touches_the_oracle():
     assert not offenders, offenders
     out = os.popen(f"ldd {os.path.join(pkg, 'lib', 'libfts_b200.so')}").read()
     assert "oracle" not in out
+
+
+# ------------------------------------------------------------------ the Julia shim (static check) ---
+JULIA_DIR = os.path.join(ROOT, "fasttanhsinhquadrature.jl_b200", "julia", "FastTanhSinhQuadratureB200")
+
+
+def _split_top(text):
+    """split on commas that are outside (), {} and []"""
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur.strip())
+    return parts
+
+
+def _julia_ccalls(src):
+    """-> [(symbol, number of argument types, number of arguments passed)] of every ccall((:sym, LIB[]), ret, (types...), args...)"""
+    out = []
+    for m in re.finditer(r"ccall\(\(:(fts_\w+),\s*LIB(?:\[\])?\),", src):
+        i, depth = m.end(), 1                     # inside ccall( ... ): find its closing parenthesis
+        j = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        parts = _split_top(src[i:j - 1])         # ret, (types...), args...
+        types = parts[1].strip()
+        assert types.startswith("(") and types.endswith(")"), (m.group(1), types)
+        tl = _split_top(types[1:-1])
+        out.append((m.group(1), len(tl), len(parts) - 2, tl, parts[0].strip()))
+    return out
+
+
+def _c_class(param):
+    """width class of a C parameter declaration of the header"""
+    t = param.strip()
+    if "*" in t or re.search(r"\bfts_(cache|integrand|tables)\b", t):
+        return "ptr"
+    t = re.sub(r"\s*\b\w+$", "", t).replace("const", "").strip()  # drop the parameter name
+    return {"int": "i32", "int32_t": "i32", "fts_dtype": "i32", "int64_t": "i64", "uint64_t": "i64", "long long": "i64", "size_t": "usize",
+            "double": "f64", "float": "f32", "unsigned": "i32", "unsigned int": "i32"}[t]
+
+
+def _jl_class(t):
+    t = t.strip()
+    if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+        return "ptr"
+    return {"Cint": "i32", "Int32": "i32", "Cuint": "i32", "Int64": "i64", "UInt64": "i64", "Csize_t": "usize", "Cdouble": "f64", "Cfloat": "f32"}[t]
+
+
+def test_julia_shim_binds_the_declared_entry_points(fts):
+    """Julia is not in the image, so the shim cannot be executed here: check statically that every `ccall` names an
+    exported entry point of include/fts_b200.h with the header's parameter count (and passes as many arguments as it
+    declares types), that the shim exports the reference's 21 names, and that its family ids are the header's."""
+    from fts_b200 import _lib
+    src = open(os.path.join(JULIA_DIR, "src", "FastTanhSinhQuadratureB200.jl")).read()
+    protos = {}
+    for ret, name, params in re.findall(r"^\s*(int|size_t|int64_t)\s+(fts_\w+)\s*\(([^;]*?)\)\s*;", HEADER, flags=re.M | re.S):
+        params = re.sub(r"/\*.*?\*/", "", params, flags=re.S).strip()
+        protos[name] = (ret, [] if params in ("", "void") else [_c_class(q) for q in _split_top(params)])
+    calls = _julia_ccalls(src)
+    assert len(calls) >= 20
+    doc_calls = _julia_ccalls(open(os.path.join(ROOT, "INTEGRATION.md")).read())  # the bindings shown to a maintainer
+    assert len(doc_calls) >= 6
+    calls = calls + doc_calls
+    lib = C.CDLL(_lib.LIB_PATH)
+    for sym, ntypes, nargs, types, ret in calls:
+        assert sym in protos and hasattr(lib, sym), f"{sym}: not an exported entry point"
+        cret, cparams = protos[sym]
+        assert ntypes == len(cparams), f"{sym}: ccall declares {ntypes} argument types, the header {len(cparams)} parameters"
+        assert nargs == ntypes, f"{sym}: {nargs} arguments passed for {ntypes} declared types"
+        assert [_jl_class(t) for t in types] == cparams, f"{sym}: {types} against {cparams}"
+        assert _jl_class(ret) == {"int": "i32", "size_t": "usize", "int64_t": "i64"}[cret], (sym, ret, cret)
+    exported = set(re.findall(r"\b\w+\b", re.search(r"^export (.*?)\n\n", src, flags=re.M | re.S).group(1)))
+    assert set(fts.REFERENCE_EXPORTS) <= exported, set(fts.REFERENCE_EXPORTS) - exported
+    ids = dict((k, int(v)) for k, v in re.findall(r":(\w+) => (\d+)", re.search(r"const FAMILY_IDS = Dict\((.*?)\)\n", src, flags=re.S).group(1)))
+    assert ids == dict(fts.FAMILIES), set(ids.items()) ^ set(dict(fts.FAMILIES).items())
+    enums = dict((k, int(v, 0)) for k, v in re.findall(r"\b(FTS_[A-Z0-9_]+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", HEADER))
+    jl = dict(re.findall(r"const ((?:\w+, )*\w+) = ((?:\w+\(\d+\), )*\w+\(\d+\))", src))
+    consts = {}
+    for names, vals in jl.items():
+        for n, v in zip(names.split(", "), re.findall(r"\((\d+)\)", vals)):
+            consts[n] = int(v)
+    for jn, hn in (("FTS_F32", "FTS_F32"), ("FTS_F64", "FTS_F64"), ("FTS_DD64", "FTS_DD64"), ("ORDER_REFERENCE", "FTS_ORDER_REFERENCE"), ("ORDER_FAST", "FTS_ORDER_FAST"),
+                   ("OPT_QUAD_EDGE_RULES", "FTS_OPT_QUAD_EDGE_RULES"), ("OPT_FORCE_DEPTH", "FTS_OPT_FORCE_DEPTH"), ("FLAG_CONVERGED", "FTS_FLAG_CONVERGED"),
+                   ("FLAG_MAX_LEVELS", "FTS_FLAG_MAX_LEVELS"), ("KIND_1D", "FTS_KIND_1D"), ("KIND_2D", "FTS_KIND_2D"), ("KIND_3D", "FTS_KIND_3D"),
+                   ("KIND_1D_CMPL", "FTS_KIND_1D_CMPL"), ("KIND_2D_CMPL", "FTS_KIND_2D_CMPL")):
+        assert consts[jn] == enums[hn], (jn, consts.get(jn), enums.get(hn))
+    # the Integrals.jl extension is registered and only calls names the shim defines
+    toml = open(os.path.join(JULIA_DIR, "Project.toml")).read()
+    assert "FastTanhSinhQuadratureB200IntegralsExt" in toml and os.path.exists(os.path.join(JULIA_DIR, "ext", "FastTanhSinhQuadratureB200IntegralsExt.jl"))
+    ext = open(os.path.join(JULIA_DIR, "ext", "FastTanhSinhQuadratureB200IntegralsExt.jl")).read()
+    for name in set(re.findall(r"FTS\.(\w+)", ext)):
+        assert re.search(rf"^(?:function |struct |const )?{name}\b", src, flags=re.M), name
+    for a, b in ("()", "[]", "{}"):
+        assert src.count(a) == src.count(b) and ext.count(a) == ext.count(b)
