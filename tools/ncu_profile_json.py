@@ -34,7 +34,7 @@ M = {"time_us": "gpu__time_duration.sum", "dfma": "smsp__sass_thread_inst_execut
      "stall_short_scoreboard": "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
      "stall_long_scoreboard": "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
      "smem_wavefronts": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"}
-SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3, "second": 1e6}
+SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "msecond": 1e3, "ms": 1e3, "usecond": 1.0, "us": 1.0, "nsecond": 1e-3, "ns": 1e-3, "second": 1e6, "s": 1e6}
 
 
 def num(v, unit):
