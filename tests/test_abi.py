@@ -95,6 +95,29 @@ def test_product_never_touches_the_oracle():
     assert "oracle" not in out
 
 
+def test_header_is_plain_c_and_links(fts, tmp_path):
+    """include/fts_b200.h is the boundary a foreign host binds: it must compile as strict C99 (no C++-isms, no torch or
+    CUDA types) and a C program must link against the library through it."""
+    import subprocess
+    from fts_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('#include "fts_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    double x[4], w[4], h; char msg[256];\n'
+                   '    if (fts_abi_version() != FTS_ABI_VERSION) return 1;\n'
+                   '    if (fts_tanhsinh(FTS_F64, 8, 1, x, w, &h) != FTS_OK) return 2;   /* host-side table generation needs no GPU */\n'
+                   '    fts_last_error(msg, sizeof msg);\n'
+                   '    printf("%.17g %.17g %.17g\\n", x[0], w[0], h);\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lfts_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    xs, ws, h = fts.tanhsinh(np.float64, 8)
+    assert [float(v) for v in out] == [float(xs[0]), float(ws[0]), float(h)]
+
+
 # ------------------------------------------------------------------ the Julia shim (static check) ---
 JULIA_DIR = os.path.join(ROOT, "fasttanhsinhquadrature.jl_b200", "julia", "FastTanhSinhQuadratureB200")
 
